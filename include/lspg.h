@@ -1,0 +1,120 @@
+/*
+ * lspg.h - C ABI of the B200-native Feature2Face generator (LiveSpeechPortraits render hot path).
+ *
+ * The reference has no native code and no FFI: its "plugin boundary" for this path is the Python class
+ * models/feature2face_G.py:Feature2Face_G (ctor(opt) :8-21, forward(input) :27-34) held by
+ * models/feature2face_model.py:Feature2FaceModel (ctor :22-27, inference() :225-237) and fed by
+ * models/base_model.py:load_networks (:193-223, state_dict in) / eval() (:108-113).
+ * Each entry point below names the reference call it stands in for.  A Python `nn.Module` shim
+ * (livespeechportraits_b200/generator.py) binds these with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions: plain C types only; every function returns 0 on success or a negative LSPG_E* code and
+ * records a message retrievable with lspg_last_error() (thread-local).  No CPU compute path exists:
+ * forward needs an sm_100 device and fails loudly otherwise.  One handle per device; calls on one handle
+ * must be serialised by the caller.  All device work is enqueued on the caller's stream; nothing
+ * synchronises or allocates inside lspg_forward once the (B,H,W,mode,workspace) plan is cached.
+ */
+#ifndef LSPG_H_
+#define LSPG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LSPG_OK 0
+#define LSPG_EINVAL (-1)     /* bad argument / unsupported shape */
+#define LSPG_ENODEV (-2)     /* no sm_100 device / host-only handle */
+#define LSPG_ECUDA (-3)      /* CUDA runtime or driver error */
+#define LSPG_ESTATE (-4)     /* weights not loaded, workspace too small, ... */
+#define LSPG_ENOMEM (-5)
+
+/* opt.size values that reach this path (models/feature2face_G.py:16-21; 'small' is out of scope) */
+#define LSPG_VARIANT_NORMAL 0
+#define LSPG_VARIANT_LARGE 1
+
+/* Precision modes.  FAST: bf16 operands, fp32 accumulate (1 MMA / K step).
+ * PARITY: bf16 hi+lo split operands, hi*hi + hi*lo + lo*hi, fp32 accumulate (3 MMAs / K step);
+ * this is the mode that meets the 1e-3 max-abs contract against the fp32 reference. */
+#define LSPG_MODE_FAST 0
+#define LSPG_MODE_PARITY 1
+
+typedef struct lspg_ctx* lspg_handle;
+
+/* One state_dict entry (models/base_model.py:208-219 hands exactly these to load_state_dict).
+ * `name` uses the reference key grammar without the DataParallel "module." prefix, e.g.
+ * "netG.model.model.0.weight"; data is host memory, fp32, contiguous (conv weights OIHW). */
+typedef struct lspg_tensor {
+  const char* name;
+  const float* data;
+  int64_t numel;
+} lspg_tensor;
+
+/* Replaces Feature2Face_G.__init__ (models/feature2face_G.py:8-21) + networks.init_net's device move
+ * (models/networks.py:392-394).  device >= 0: CUDA ordinal, must be compute capability 10.x.
+ * device == -1: host-only handle for plan/packing introspection (lspg_forward returns LSPG_ENODEV). */
+int lspg_create(lspg_handle* out, int variant, int ngf, int num_downs, int in_nc, int out_nc, int device);
+
+/* Replaces net.load_state_dict(state_dict, strict=False) (models/base_model.py:219) and the eval-mode
+ * BatchNorm semantics of BaseModel.eval() (:108-113): folds running stats into per-channel scale/shift
+ * (eps 1e-5), packs conv weights into the K-major tap/phase layout the kernels read, uploads them.
+ * Keys that are absent keep their previous value (strict=False); unknown keys are ignored;
+ * a known key with the wrong element count is LSPG_EINVAL. */
+int lspg_load_weights(lspg_handle h, const lspg_tensor* tensors, int n);
+
+/* Bytes of caller-owned device workspace lspg_forward needs for this problem size and mode. */
+int lspg_workspace_bytes(lspg_handle h, int batch, int height, int width, int mode, size_t* out);
+
+/* Replaces Feature2FaceModel.inference's cat + G call (models/feature2face_model.py:231-233) and
+ * Feature2Face_G.forward (models/feature2face_G.py:27-34), eval mode, opt.fp16 == 0.
+ *   feature_map: device fp32 [B,1,H,W], batch stride fm_bstride elements
+ *   cand:        device fp32 [B,12,H,W], batch stride cand_bstride elements (0 = one candidate set for
+ *                every frame, as demo.py:266 does)
+ *   out:         device fp32 [B,3,H,W] contiguous, values in (-1,1)
+ * A single [B,13,H,W] tensor x is passed as feature_map=x, cand=x+H*W, both strides 13*H*W.
+ * H and W must be multiples of 256 (8 stride-2 stages).  Asynchronous on `stream` (a cudaStream_t). */
+int lspg_forward(lspg_handle h, const float* feature_map, int64_t fm_bstride, const float* cand,
+                 int64_t cand_bstride, float* out, int batch, int height, int width, void* workspace,
+                 size_t workspace_bytes, int mode, void* stream);
+
+/* Replaces nothing in the reference (module garbage collection). */
+int lspg_destroy(lspg_handle h);
+
+const char* lspg_last_error(void);
+
+/* ---- introspection (tests, bench accounting; no compute) ------------------------------------------ */
+
+typedef struct lspg_layer_info {
+  int kind;                 /* 0 head, 1 stride-1, 2 stride-2, 3 upsample-phase, 4 tail */
+  int n_src, src[2], cin[2];/* activation tensor ids and channels of the concat sources */
+  int out, res;             /* output / residual tensor ids (-1 = none; tail writes the user buffer) */
+  int cout, cout_pad;
+  int n_phases, n_taps, k_total; /* packed weights: [n_phases][cout_pad][k_total] */
+  int relu, has_bn;
+  int8_t tap_map[4][9], tap_dx[4][9], tap_dy[4][9];
+  char conv_key[96];        /* state-dict key prefix of the conv (".weight" appended) */
+  char bn_key[96];          /* "" when the conv has no BatchNorm */
+} lspg_layer_info;
+
+int lspg_num_layers(lspg_handle h, int* out);
+int lspg_layer_info_get(lspg_handle h, int layer, lspg_layer_info* out);
+/* Packed weights as the kernels see them: bf16 bit patterns, limb 0 = hi, limb 1 = lo (w - hi);
+ * `count` must be n_phases*cout_pad*k_total.  scale/shift: cout_pad floats each. */
+int lspg_layer_packed(lspg_handle h, int layer, int limb, uint16_t* dst, int64_t count);
+int lspg_layer_affine(lspg_handle h, int layer, float* scale, float* shift, int64_t count);
+/* Activation tensor table for (batch,height,width): per-image channels/height/width of tensor `id`. */
+int lspg_num_tensors(lspg_handle h, int* out);
+int lspg_tensor_shape(lspg_handle h, int id, int height, int width, int* c, int* th, int* tw);
+/* Copy activation tensor `id` (bf16 NHWC, limb 0 or 1) of the most recent forward to host memory. */
+int lspg_debug_read_tensor(lspg_handle h, int id, int limb, uint16_t* dst, int64_t count);
+/* Kernels one lspg_forward call launches (for bench.py's gpu_launches accounting). */
+int lspg_launches_per_forward(lspg_handle h, int* out);
+/* Algorithmic conv FLOPs per frame (2*MAC of the reference convs) at height x width. */
+int lspg_flops_per_frame(lspg_handle h, int height, int width, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LSPG_H_ */

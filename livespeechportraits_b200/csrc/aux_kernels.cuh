@@ -1,0 +1,65 @@
+// Memory-bound helper kernels around the conv stack.
+#pragma once
+#include <cuda_bf16.h>
+#include <cstdint>
+
+namespace lspg {
+
+// Input packer: fuses Feature2FaceModel.inference's torch.cat([feature_map, cand_image], 1)
+// (reference models/feature2face_model.py:231), the NCHW->NHWC transpose, the fp32->bf16 conversion (hi and,
+// in parity mode, lo limb) and a 2x2 space-to-depth, so that the stride-2 head conv (13->64,
+// models/networks.py:594-595 with input_nc=13) becomes a 4-tap stride-1 conv over a 64-channel tensor:
+//   S[n, oy, ox, (py*2+px)*16 + c] = x[n, c, 2*oy+py, 2*ox+px]   (c < in_nc; channels in_nc..15 are zero)
+// One thread per output pixel: float2 reads are coalesced along W per channel plane; each thread writes its
+// 128-byte NHWC row.  HBM-bound: 4*in_nc*H*W bytes in, 2*NL*16*H*W bytes out per frame.
+template <int NL>
+__global__ void pack_input_s2d_kernel(const float* __restrict__ fm, long long fm_bstride,
+                                      const float* __restrict__ cand, long long cand_bstride, int in_nc,
+                                      __nv_bfloat16* __restrict__ dst, long long limb_stride, int batch, int height,
+                                      int width) {
+  const int wo = width >> 1, ho = height >> 1;
+  const long long total = static_cast<long long>(batch) * ho * wo;
+  const long long plane = static_cast<long long>(height) * width;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ox = static_cast<int>(i % wo);
+    const long long r = i / wo;
+    const int oy = static_cast<int>(r % ho);
+    const int n = static_cast<int>(r / ho);
+    uint32_t hi[32], lo[32];   // 64 channels packed as bf16 pairs
+#pragma unroll
+    for (int k = 0; k < 32; ++k) { hi[k] = 0u; lo[k] = 0u; }
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      if (c < in_nc) {
+        const float* src = (c == 0) ? fm + n * fm_bstride : cand + n * cand_bstride + (c - 1) * plane;
+#pragma unroll
+        for (int py = 0; py < 2; ++py) {
+          const float2 v = *reinterpret_cast<const float2*>(src + static_cast<long long>(2 * oy + py) * width + 2 * ox);
+          const float vv[2] = {v.x, v.y};
+#pragma unroll
+          for (int px = 0; px < 2; ++px) {
+            const int ch = (py * 2 + px) * 16 + c;
+            const __nv_bfloat16 h = __float2bfloat16_rn(vv[px]);
+            const uint32_t hb = static_cast<uint32_t>(__bfloat16_as_ushort(h));
+            hi[ch >> 1] |= hb << ((ch & 1) * 16);
+            if (NL == 2) {
+              const __nv_bfloat16 l = __float2bfloat16_rn(vv[px] - __bfloat162float(h));
+              lo[ch >> 1] |= static_cast<uint32_t>(__bfloat16_as_ushort(l)) << ((ch & 1) * 16);
+            }
+          }
+        }
+      }
+    }
+    uint4* d = reinterpret_cast<uint4*>(dst + i * 64);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) d[k] = make_uint4(hi[4 * k], hi[4 * k + 1], hi[4 * k + 2], hi[4 * k + 3]);
+    if (NL == 2) {
+      uint4* d2 = reinterpret_cast<uint4*>(dst + limb_stride + i * 64);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) d2[k] = make_uint4(lo[4 * k], lo[4 * k + 1], lo[4 * k + 2], lo[4 * k + 3]);
+    }
+  }
+}
+
+}  // namespace lspg

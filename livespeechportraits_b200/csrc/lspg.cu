@@ -1,0 +1,847 @@
+// C-ABI implementation of the B200-native Feature2Face generator (see include/lspg.h).
+//
+// Host side: network structure (mirrors models/networks.py:554-675 of the reference), weight packing with
+// eval-BatchNorm folding, activation-tensor planning, TMA descriptor construction, launch sequencing.
+// Device side: conv_umma.cuh (tcgen05/TMA implicit-GEMM conv) and aux_kernels.cuh (input packer).
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/lspg.h"
+#include "aux_kernels.cuh"
+#include "conv_umma.cuh"
+
+namespace {
+
+using namespace lspg;
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                         \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) return fail(LSPG_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+enum Kind { K_HEAD = 0, K_S1 = 1, K_S2 = 2, K_UP = 3, K_TAIL = 4 };
+
+uint16_t f32_to_bf16(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7F800000u) == 0x7F800000u) return static_cast<uint16_t>(u >> 16);   // inf / nan: truncate
+  u += 0x7FFFu + ((u >> 16) & 1u);                                                // round to nearest even
+  return static_cast<uint16_t>(u >> 16);
+}
+float bf16_to_f32(uint16_t h) {
+  uint32_t u = static_cast<uint32_t>(h) << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+struct TensorInfo {
+  int channels;
+  int shift;       // per-image spatial extent = (H >> shift, W >> shift)
+};
+
+struct Layer {
+  int kind = K_S1;
+  int n_src = 1;
+  int src[2] = {-1, -1};
+  int cin[2] = {0, 0};
+  int out = -1, res = -1;
+  int cout = 0, cout_pad = 0;
+  int n_phases = 1, n_taps = 9, k_total = 0;
+  int relu = 0, has_bn = 0;
+  int grid_shift = 0;            // sampling grid = (H >> grid_shift, W >> grid_shift)
+  int8_t tap_map[4][kMaxTaps] = {}, tap_dx[4][kMaxTaps] = {}, tap_dy[4][kMaxTaps] = {};
+  std::string conv_key, bn_key;
+  // parameters (host, fp32, as loaded) and their packed forms
+  std::vector<float> w;                      // OIHW
+  std::vector<float> bn_w, bn_b, bn_m, bn_v;
+  std::vector<uint16_t> packed[2];           // [limb][phase][cout_pad][k_total]
+  std::vector<float> scale, shift;           // [cout_pad]
+  bool dirty = true;
+  // device copies
+  uint16_t* d_w = nullptr;                   // [limb][phase][cout_pad][k_total]
+  float* d_scale = nullptr;
+  float* d_shift = nullptr;
+};
+
+struct PlanLayer {
+  ConvParams prm;
+  int bn = 64;
+  int grid = 1;
+};
+
+struct Plan {
+  int batch = 0, height = 0, width = 0, mode = 0;
+  void* workspace = nullptr;
+  std::vector<size_t> tensor_off;            // byte offset of limb 0 of each activation tensor
+  std::vector<size_t> tensor_limb_stride;    // bytes between limbs
+  std::vector<PlanLayer> layers;
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+}  // namespace
+
+struct lspg_ctx {
+  int variant = 0, ngf = 64, num_downs = 8, in_nc = 13, out_nc = 3, device = -1;
+  int num_sms = 0;
+  std::vector<TensorInfo> tensors;
+  std::vector<Layer> layers;
+  bool weights_loaded = false;
+  EncodeTiledFn encode = nullptr;
+  std::map<std::tuple<int, int, int, int, void*>, std::unique_ptr<Plan>> plans;
+  Plan* last_plan = nullptr;
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// Network structure.  Mirrors ResUnetSkipConnectionBlock[_small].__init__ (models/networks.py:585-640 /
+// 489-544): nn.Sequential positions give the state-dict keys; execution order gives the layer list.
+// ------------------------------------------------------------------------------------------------
+struct BlockKeys {
+  std::string down, down_bn, up, up_bn, sub;
+  std::vector<std::string> res_down, res_up;
+};
+
+BlockKeys block_keys(const std::string& prefix, bool outer, bool inner, int nres) {
+  BlockKeys b;
+  int i = 0;
+  auto at = [&](int k) { return prefix + "." + std::to_string(k); };
+  b.down = at(i++);
+  if (!outer && !inner) b.down_bn = at(i++);
+  i++;  // ReLU
+  for (int r = 0; r < nres; ++r) b.res_down.push_back(at(i++));
+  if (!inner) b.sub = at(i++) + ".model";
+  i++;  // Upsample
+  b.up = at(i++);
+  if (!outer) {
+    b.up_bn = at(i++);
+    i++;  // ReLU
+    for (int r = 0; r < nres; ++r) b.res_up.push_back(at(i++));
+  }
+  return b;
+}
+
+void set_taps_s1(Layer& L) {
+  L.n_phases = 1;
+  L.n_taps = 9;
+  for (int r = 0; r < 3; ++r)
+    for (int s = 0; s < 3; ++s) {
+      L.tap_map[0][r * 3 + s] = 0;
+      L.tap_dx[0][r * 3 + s] = static_cast<int8_t>(s - 1);
+      L.tap_dy[0][r * 3 + s] = static_cast<int8_t>(r - 1);
+    }
+}
+
+// stride-2, pad-1: input row 2*oy + r - 1 = 2*(oy + d) + parity
+void s2_row(int r, int* parity, int* d) {
+  if (r == 0) { *parity = 1; *d = -1; }
+  else if (r == 1) { *parity = 0; *d = 0; }
+  else { *parity = 1; *d = 0; }
+}
+
+void set_taps_s2(Layer& L) {
+  L.n_phases = 1;
+  L.n_taps = 9;
+  for (int r = 0; r < 3; ++r)
+    for (int s = 0; s < 3; ++s) {
+      int py, dy, px, dx;
+      s2_row(r, &py, &dy);
+      s2_row(s, &px, &dx);
+      L.tap_map[0][r * 3 + s] = static_cast<int8_t>(py * 2 + px);
+      L.tap_dx[0][r * 3 + s] = static_cast<int8_t>(dx);
+      L.tap_dy[0][r * 3 + s] = static_cast<int8_t>(dy);
+    }
+}
+
+// nearest-x2 upsample followed by 3x3 pad-1: output row 2*i + parity reads upsampled rows
+// 2*i + parity + r - 1, i.e. source rows i + d.  Returns d for (parity, r).
+int up_row(int parity, int r) {
+  if (parity == 0) return r == 0 ? -1 : 0;
+  return r == 2 ? 1 : 0;
+}
+
+void set_taps_up(Layer& L) {
+  L.n_phases = 4;
+  L.n_taps = 4;
+  for (int py = 0; py < 2; ++py)
+    for (int px = 0; px < 2; ++px)
+      for (int ty = 0; ty < 2; ++ty)
+        for (int tx = 0; tx < 2; ++tx) {
+          const int z = py * 2 + px, t = ty * 2 + tx;
+          L.tap_map[z][t] = 0;
+          L.tap_dy[z][t] = static_cast<int8_t>(py == 0 ? ty - 1 : ty);
+          L.tap_dx[z][t] = static_cast<int8_t>(px == 0 ? tx - 1 : tx);
+        }
+}
+
+void set_taps_head(Layer& L) {
+  L.n_phases = 1;
+  L.n_taps = 4;
+  for (int ty = 0; ty < 2; ++ty)
+    for (int tx = 0; tx < 2; ++tx) {
+      L.tap_map[0][ty * 2 + tx] = 0;
+      L.tap_dy[0][ty * 2 + tx] = static_cast<int8_t>(ty - 1);
+      L.tap_dx[0][ty * 2 + tx] = static_cast<int8_t>(tx - 1);
+    }
+}
+
+void set_taps_tail(Layer& L) {
+  L.n_phases = 1;
+  L.n_taps = 9;
+  for (int ty = 0; ty < 3; ++ty)
+    for (int tx = 0; tx < 3; ++tx) {
+      L.tap_map[0][ty * 3 + tx] = 0;
+      L.tap_dy[0][ty * 3 + tx] = static_cast<int8_t>(ty - 1);
+      L.tap_dx[0][ty * 3 + tx] = static_cast<int8_t>(tx - 1);
+    }
+}
+
+int build_network(lspg_ctx* h) {
+  const int D = h->num_downs, ngf = h->ngf;
+  const int nres = h->variant == LSPG_VARIANT_LARGE ? 2 : 1;
+  std::vector<std::pair<int, int>> levels;   // (outer_nc, inner_nc), outermost first; networks.py:558-571
+  levels.push_back({h->out_nc, ngf});
+  levels.push_back({ngf, ngf * 2});
+  levels.push_back({ngf * 2, ngf * 4});
+  levels.push_back({ngf * 4, ngf * 8});
+  for (int i = 0; i < D - 5; ++i) levels.push_back({ngf * 8, ngf * 8});
+  levels.push_back({ngf * 8, ngf * 8});
+
+  auto new_tensor = [&](int c, int shift) {
+    h->tensors.push_back({c, shift});
+    return static_cast<int>(h->tensors.size()) - 1;
+  };
+  auto add_res = [&](const std::string& key, int x, int c, int shift) {
+    // ResidualBlock (networks.py:662-674): conv-BN-ReLU, conv-BN, += x, ReLU
+    Layer a;
+    a.kind = K_S1; a.n_src = 1; a.src[0] = x; a.cin[0] = c; a.cout = a.cout_pad = c;
+    a.relu = 1; a.has_bn = 1; a.grid_shift = shift;
+    a.conv_key = key + ".block.0"; a.bn_key = key + ".block.1";
+    set_taps_s1(a); a.k_total = 9 * c; a.out = new_tensor(c, shift);
+    h->layers.push_back(a);
+    Layer b = a;
+    b.src[0] = a.out; b.res = x; b.conv_key = key + ".block.3"; b.bn_key = key + ".block.4";
+    b.out = new_tensor(c, shift);
+    h->layers.push_back(b);
+    return b.out;
+  };
+
+  const int s_in = new_tensor(64, 1);        // tensor 0: space-to-depth packed input (aux_kernels.cuh)
+
+  // recursive emission in execution order; returns the id of d_l (the block's up-path result)
+  std::function<int(int, int, const std::string&)> emit = [&](int l, int x, const std::string& prefix) -> int {
+    const bool outer = (l == 0), inner = (l == D - 1);
+    const int outer_nc = levels[l].first, inner_nc = levels[l].second;
+    const BlockKeys k = block_keys(prefix, outer, inner, nres);
+    Layer dn;
+    dn.cout = dn.cout_pad = inner_nc; dn.relu = 1; dn.grid_shift = l + 1;
+    dn.conv_key = k.down; dn.bn_key = k.down_bn; dn.has_bn = k.down_bn.empty() ? 0 : 1;
+    if (outer) {
+      dn.kind = K_HEAD; dn.n_src = 1; dn.src[0] = s_in; dn.cin[0] = 64; set_taps_head(dn); dn.k_total = 4 * 64;
+    } else {
+      dn.kind = K_S2; dn.n_src = 1; dn.src[0] = x; dn.cin[0] = outer_nc; set_taps_s2(dn); dn.k_total = 9 * outer_nc;
+    }
+    dn.out = new_tensor(inner_nc, l + 1);
+    h->layers.push_back(dn);
+    int e = dn.out;
+    for (const auto& rk : k.res_down) e = add_res(rk, e, inner_nc, l + 1);
+    int d = -1;
+    if (!inner) d = emit(l + 1, e, k.sub);
+    Layer up;
+    up.n_src = inner ? 1 : 2; up.src[0] = e; up.cin[0] = inner_nc;
+    if (!inner) { up.src[1] = d; up.cin[1] = inner_nc; }
+    up.grid_shift = l + 1;                    // sampling grid = source grid
+    up.conv_key = k.up; up.bn_key = k.up_bn; up.has_bn = k.up_bn.empty() ? 0 : 1;
+    if (outer) {
+      up.kind = K_TAIL; up.cout = outer_nc; up.cout_pad = 16; up.relu = 0; set_taps_tail(up);
+      up.k_total = 9 * up.n_src * inner_nc; up.out = -1;
+      h->layers.push_back(up);
+      return -1;
+    }
+    up.kind = K_UP; up.cout = up.cout_pad = outer_nc; up.relu = 1; set_taps_up(up);
+    up.k_total = 4 * up.n_src * inner_nc; up.out = new_tensor(outer_nc, l);
+    h->layers.push_back(up);
+    int dd = up.out;
+    for (const auto& rk : k.res_up) dd = add_res(rk, dd, outer_nc, l);
+    return dd;
+  };
+  emit(0, -1, "netG.model.model");
+  return LSPG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight packing: OIHW fp32 -> [phase][cout_pad][K] (K = tap-major, then concat source, then channel),
+// BatchNorm folded into fp32 scale/shift that the epilogue applies (the weights themselves are NOT scaled,
+// so operand rounding matches "conv then BN").
+// ------------------------------------------------------------------------------------------------
+void pack_layer(lspg_ctx* h, Layer& L) {
+  const int cin_total = (L.kind == K_HEAD) ? h->in_nc : (L.cin[0] + (L.n_src == 2 ? L.cin[1] : 0));
+  const size_t per_phase = static_cast<size_t>(L.cout_pad) * L.k_total;
+  std::vector<float> P(per_phase * L.n_phases, 0.0f);
+  auto W = [&](int o, int c, int r, int s) -> float {
+    return L.w[((static_cast<size_t>(o) * cin_total + c) * 3 + r) * 3 + s];
+  };
+  const int kb_per_tap = (L.cin[0] + (L.n_src == 2 ? L.cin[1] : 0));   // K elements per tap
+  auto kidx = [&](int tap, int c_concat) { return tap * kb_per_tap + c_concat; };
+
+  if (L.kind == K_S1 || L.kind == K_S2) {
+    for (int o = 0; o < L.cout; ++o)
+      for (int r = 0; r < 3; ++r)
+        for (int s = 0; s < 3; ++s)
+          for (int c = 0; c < cin_total; ++c)
+            P[static_cast<size_t>(o) * L.k_total + kidx(r * 3 + s, c)] = W(o, c, r, s);
+  } else if (L.kind == K_UP) {
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px) {
+        float* Pz = P.data() + per_phase * (py * 2 + px);
+        for (int o = 0; o < L.cout; ++o)
+          for (int r = 0; r < 3; ++r)
+            for (int s = 0; s < 3; ++s) {
+              const int ty = up_row(py, r) - (py == 0 ? -1 : 0);   // dy -> tap row index (see set_taps_up)
+              const int tx = up_row(px, s) - (px == 0 ? -1 : 0);
+              for (int c = 0; c < cin_total; ++c)
+                Pz[static_cast<size_t>(o) * L.k_total + kidx(ty * 2 + tx, c)] += W(o, c, r, s);
+            }
+      }
+  } else if (L.kind == K_HEAD) {
+    // source channel (py*2+px)*16 + c of the space-to-depth input, taps (dy,dx) in {-1,0}^2
+    for (int o = 0; o < L.cout; ++o)
+      for (int r = 0; r < 3; ++r)
+        for (int s = 0; s < 3; ++s) {
+          int py, dy, px, dx;
+          s2_row(r, &py, &dy);
+          s2_row(s, &px, &dx);
+          const int tap = (dy + 1) * 2 + (dx + 1);
+          for (int c = 0; c < cin_total; ++c)
+            P[static_cast<size_t>(o) * L.k_total + kidx(tap, (py * 2 + px) * 16 + c)] = W(o, c, r, s);
+        }
+  } else {  // K_TAIL: row n = (py*2+px)*out_nc + c, taps (dy,dx) in {-1,0,1}^2 on the source grid
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px)
+        for (int o = 0; o < L.cout; ++o) {
+          const int n = (py * 2 + px) * L.cout + o;
+          for (int r = 0; r < 3; ++r)
+            for (int s = 0; s < 3; ++s) {
+              const int tap = (up_row(py, r) + 1) * 3 + (up_row(px, s) + 1);
+              for (int c = 0; c < cin_total; ++c)
+                P[static_cast<size_t>(n) * L.k_total + kidx(tap, c)] += W(o, c, r, s);
+            }
+        }
+  }
+  for (int l = 0; l < 2; ++l) L.packed[l].assign(P.size(), 0);
+  for (size_t i = 0; i < P.size(); ++i) {
+    const uint16_t hi = f32_to_bf16(P[i]);
+    L.packed[0][i] = hi;
+    L.packed[1][i] = f32_to_bf16(P[i] - bf16_to_f32(hi));
+  }
+  L.scale.assign(L.cout_pad, 1.0f);
+  L.shift.assign(L.cout_pad, 0.0f);
+  if (L.has_bn) {
+    for (int o = 0; o < L.cout; ++o) {
+      const float inv = 1.0f / sqrtf(L.bn_v[o] + 1e-5f);   // eval-mode BatchNorm2d, eps = torch default
+      L.scale[o] = L.bn_w[o] * inv;
+      L.shift[o] = L.bn_b[o] - L.bn_m[o] * L.scale[o];
+    }
+  }
+}
+
+int upload_layer(lspg_ctx* h, Layer& L) {
+  if (h->device < 0) return LSPG_OK;
+  const size_t n = L.packed[0].size();
+  if (!L.d_w) {
+    CUDA_TRY(cudaMalloc(&L.d_w, 2 * n * sizeof(uint16_t)));
+    CUDA_TRY(cudaMalloc(&L.d_scale, L.cout_pad * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&L.d_shift, L.cout_pad * sizeof(float)));
+  }
+  CUDA_TRY(cudaMemcpy(L.d_w, L.packed[0].data(), n * 2, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(L.d_w + n, L.packed[1].data(), n * 2, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(L.d_scale, L.scale.data(), L.cout_pad * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(L.d_shift, L.shift.data(), L.cout_pad * 4, cudaMemcpyHostToDevice));
+  return LSPG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Planning
+// ------------------------------------------------------------------------------------------------
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int nl_of(int mode) { return mode == LSPG_MODE_PARITY ? 2 : 1; }
+
+size_t tensor_bytes_one_limb(const TensorInfo& t, int B, int H, int W) {
+  return static_cast<size_t>(B) * (H >> t.shift) * (W >> t.shift) * t.channels * 2;
+}
+
+size_t workspace_bytes(const lspg_ctx* h, int B, int H, int W, int mode) {
+  size_t total = 0;
+  for (const auto& t : h->tensors) total += align_up(tensor_bytes_one_limb(t, B, H, W), 1024) * nl_of(mode);
+  return total + 1024;
+}
+
+int check_shape(const lspg_ctx* h, int B, int H, int W, int mode) {
+  if (B < 1 || B > 4096) return fail(LSPG_EINVAL, "batch %d out of range", B);
+  const int m = 1 << h->num_downs;
+  if (H < m || W < m || H % m || W % m)
+    return fail(LSPG_EINVAL, "height/width must be positive multiples of %d (got %dx%d)", m, H, W);
+  if (mode != LSPG_MODE_FAST && mode != LSPG_MODE_PARITY) return fail(LSPG_EINVAL, "unknown precision mode %d", mode);
+  return LSPG_OK;
+}
+
+int ilog2(int v) {
+  int l = 0;
+  while ((1 << (l + 1)) <= v) ++l;
+  return l;
+}
+
+// 5-D activation view {C, X, Y, N, limb}; parity/phase views start at (py, px) and step 2 in X and Y.
+int make_act_map(lspg_ctx* h, CUtensorMap* m, void* base, size_t limb_stride, int NL, int C, int B, int Ht, int Wt,
+                 bool strided2, int py, int px, int tw, int th, int nb) {
+  const size_t es = 2;
+  uint8_t* p = static_cast<uint8_t*>(base);
+  cuuint64_t dims[5];
+  cuuint64_t strides[4];
+  if (!strided2) {
+    dims[0] = C; dims[1] = Wt; dims[2] = Ht; dims[3] = B; dims[4] = NL;
+    strides[0] = static_cast<cuuint64_t>(C) * es;
+    strides[1] = static_cast<cuuint64_t>(Wt) * C * es;
+  } else {
+    p += (static_cast<size_t>(py) * Wt + px) * C * es;
+    dims[0] = C; dims[1] = Wt / 2; dims[2] = Ht / 2; dims[3] = B; dims[4] = NL;
+    strides[0] = static_cast<cuuint64_t>(2) * C * es;
+    strides[1] = static_cast<cuuint64_t>(2) * Wt * C * es;
+  }
+  strides[2] = static_cast<cuuint64_t>(Ht) * Wt * C * es;
+  strides[3] = NL > 1 ? limb_stride : strides[2] * B;
+  cuuint32_t box[5] = {64u, static_cast<cuuint32_t>(tw), static_cast<cuuint32_t>(th), static_cast<cuuint32_t>(nb), 1u};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = h->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, p, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(LSPG_ECUDA, "cuTensorMapEncodeTiled(activation C=%d %dx%d B=%d box %dx%dx%d) failed: %d", C, Wt, Ht, B,
+                tw, th, nb, static_cast<int>(r));
+  return LSPG_OK;
+}
+
+int make_weight_map(lspg_ctx* h, CUtensorMap* m, const Layer& L, int bn) {
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(L.k_total), static_cast<cuuint64_t>(L.cout_pad),
+                        static_cast<cuuint64_t>(2 * L.n_phases)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(L.k_total) * 2,
+                           static_cast<cuuint64_t>(L.k_total) * L.cout_pad * 2};
+  cuuint32_t box[3] = {64u, static_cast<cuuint32_t>(bn), 1u};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = h->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, L.d_w, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(LSPG_ECUDA, "cuTensorMapEncodeTiled(weights K=%d) failed: %d", L.k_total, static_cast<int>(r));
+  return LSPG_OK;
+}
+
+uint32_t make_idesc(int bn) {
+  // cute::UMMA::InstrDescriptor bit layout: c_format[4,6)=1 (F32), a_format[7,10)=1 (BF16), b_format[10,13)=1,
+  // a/b major [15],[16] = 0 (K-major), n_dim[17,23) = N>>3, m_dim[24,29) = M>>4
+  uint32_t d = 0;
+  d |= 1u << 4;
+  d |= 1u << 7;
+  d |= 1u << 10;
+  d |= static_cast<uint32_t>(bn >> 3) << 17;
+  d |= static_cast<uint32_t>(kTileM >> 4) << 24;
+  return d;
+}
+
+int choose_bn(const Layer& L) {
+  if (L.kind == K_TAIL) return 16;
+  return (L.cout_pad % 128 == 0) ? 128 : 64;
+}
+
+int build_plan(lspg_ctx* h, Plan* P, int B, int H, int W, int mode, void* workspace) {
+  const int NL = nl_of(mode);
+  P->batch = B; P->height = H; P->width = W; P->mode = mode; P->workspace = workspace;
+  size_t off = 0;
+  const size_t base = align_up(reinterpret_cast<size_t>(workspace), 1024) - reinterpret_cast<size_t>(workspace);
+  off = base;
+  for (const auto& t : h->tensors) {
+    const size_t one = align_up(tensor_bytes_one_limb(t, B, H, W), 1024);
+    P->tensor_off.push_back(off);
+    P->tensor_limb_stride.push_back(one);
+    off += one * NL;
+  }
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  for (const Layer& L : h->layers) {
+    PlanLayer pl;
+    ConvParams& p = pl.prm;
+    memset(&p, 0, sizeof(p));
+    const int Hs = H >> L.grid_shift, Ws = W >> L.grid_shift;     // sampling grid
+    int tw = Ws < 16 ? Ws : 16;
+    int th = 128 / tw;
+    if (th > Hs) th = Hs;
+    const int nb = 128 / (tw * th);
+    pl.bn = choose_bn(L);
+    p.tw_log2 = ilog2(tw); p.th_log2 = ilog2(th);
+    p.tiles_x = Ws / tw; p.tiles_y = Hs / th; p.tiles_n = (B + nb - 1) / nb;
+    p.n_tiles = L.cout_pad / pl.bn;
+    p.n_phases = L.n_phases;
+    p.total_tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles * p.n_phases;
+    p.n_taps = L.n_taps; p.n_src = L.n_src;
+    p.chunks[0] = L.cin[0] / 64; p.chunks[1] = L.n_src == 2 ? L.cin[1] / 64 : 0;
+    p.relu = L.relu; p.has_res = L.res >= 0 ? 1 : 0;
+    p.batch = B; p.hs = Hs; p.ws = Ws;
+    p.idesc = make_idesc(pl.bn);
+    p.scale = L.d_scale; p.shift = L.d_shift; p.out_f32 = nullptr;
+    memcpy(p.tap_map, L.tap_map, sizeof(p.tap_map));
+    memcpy(p.tap_dx, L.tap_dx, sizeof(p.tap_dx));
+    memcpy(p.tap_dy, L.tap_dy, sizeof(p.tap_dy));
+    int rc;
+    // ---- source views
+    for (int s = 0; s < L.n_src; ++s) {
+      const TensorInfo& t = h->tensors[L.src[s]];
+      const int Ht = H >> t.shift, Wt = W >> t.shift;
+      void* tb = ws + P->tensor_off[L.src[s]];
+      const size_t ls = P->tensor_limb_stride[L.src[s]];
+      if (L.kind == K_S2) {
+        for (int q = 0; q < 4; ++q)
+          if ((rc = make_act_map(h, &p.a[q], tb, ls, NL, t.channels, B, Ht, Wt, true, q >> 1, q & 1, tw, th, nb))) return rc;
+      } else {
+        if ((rc = make_act_map(h, &p.a[s], tb, ls, NL, t.channels, B, Ht, Wt, false, 0, 0, tw, th, nb))) return rc;
+      }
+    }
+    // unused slots still need valid descriptors for prefetch.tensormap
+    const int used = (L.kind == K_S2) ? 4 : L.n_src;
+    for (int q = used; q < 4; ++q) p.a[q] = p.a[0];
+    if ((rc = make_weight_map(h, &p.w, L, pl.bn))) return rc;
+    // ---- output / residual views
+    if (L.kind != K_TAIL) {
+      const TensorInfo& t = h->tensors[L.out];
+      const int Ht = H >> t.shift, Wt = W >> t.shift;
+      void* tb = ws + P->tensor_off[L.out];
+      const size_t ls = P->tensor_limb_stride[L.out];
+      if (L.kind == K_UP) {
+        for (int q = 0; q < 4; ++q)
+          if ((rc = make_act_map(h, &p.out[q], tb, ls, NL, t.channels, B, Ht, Wt, true, q >> 1, q & 1, tw, th, nb))) return rc;
+      } else {
+        if ((rc = make_act_map(h, &p.out[0], tb, ls, NL, t.channels, B, Ht, Wt, false, 0, 0, tw, th, nb))) return rc;
+        for (int q = 1; q < 4; ++q) p.out[q] = p.out[0];
+      }
+      if (L.res >= 0) {
+        const TensorInfo& r = h->tensors[L.res];
+        if ((rc = make_act_map(h, &p.res, ws + P->tensor_off[L.res], P->tensor_limb_stride[L.res], NL, r.channels, B,
+                               H >> r.shift, W >> r.shift, false, 0, 0, tw, th, nb)))
+          return rc;
+      } else {
+        p.res = p.out[0];
+      }
+    } else {
+      for (int q = 0; q < 4; ++q) p.out[q] = p.a[0];
+      p.res = p.a[0];
+    }
+    pl.grid = p.total_tiles < h->num_sms ? p.total_tiles : h->num_sms;
+    P->layers.push_back(pl);
+  }
+  return LSPG_OK;
+}
+
+template <int BN, int NL, bool TAIL>
+int launch_conv(const ConvParams& p, int grid, cudaStream_t st) {
+  using Cfg = ConvCfg<BN, NL, TAIL>;
+  static bool configured = false;
+  if (!configured) {
+    CUDA_TRY(cudaFuncSetAttribute(conv_umma_kernel<BN, NL, TAIL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  Cfg::kSmemBytes));
+    configured = true;
+  }
+  conv_umma_kernel<BN, NL, TAIL><<<grid, kThreads, Cfg::kSmemBytes, st>>>(p);
+  CUDA_TRY(cudaGetLastError());
+  return LSPG_OK;
+}
+
+int launch_layer(const PlanLayer& pl, int kind, int NL, cudaStream_t st) {
+  if (kind == K_TAIL) return NL == 1 ? launch_conv<16, 1, true>(pl.prm, pl.grid, st) : launch_conv<16, 2, true>(pl.prm, pl.grid, st);
+  if (pl.bn == 128) return NL == 1 ? launch_conv<128, 1, false>(pl.prm, pl.grid, st) : launch_conv<128, 2, false>(pl.prm, pl.grid, st);
+  return NL == 1 ? launch_conv<64, 1, false>(pl.prm, pl.grid, st) : launch_conv<64, 2, false>(pl.prm, pl.grid, st);
+}
+
+}  // namespace
+
+// ====================================================================================================
+// C ABI
+// ====================================================================================================
+extern "C" {
+
+const char* lspg_last_error(void) { return g_err.c_str(); }
+
+int lspg_create(lspg_handle* out, int variant, int ngf, int num_downs, int in_nc, int out_nc, int device) {
+  if (!out) return fail(LSPG_EINVAL, "out is NULL");
+  *out = nullptr;
+  if (variant != LSPG_VARIANT_NORMAL && variant != LSPG_VARIANT_LARGE)
+    return fail(LSPG_EINVAL, "variant %d not supported (opt.size 'normal' or 'large')", variant);
+  if (ngf < 64 || ngf % 64) return fail(LSPG_EINVAL, "ngf must be a multiple of 64 (got %d)", ngf);
+  if (num_downs < 5 || num_downs > 10) return fail(LSPG_EINVAL, "num_downs %d out of range [5,10]", num_downs);
+  if (in_nc < 1 || in_nc > 16) return fail(LSPG_EINVAL, "in_nc %d out of range [1,16]", in_nc);
+  if (out_nc != 3) return fail(LSPG_EINVAL, "out_nc must be 3 (got %d)", out_nc);
+  std::unique_ptr<lspg_ctx> h(new lspg_ctx);
+  h->variant = variant; h->ngf = ngf; h->num_downs = num_downs; h->in_nc = in_nc; h->out_nc = out_nc; h->device = device;
+  if (device >= 0) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) return fail(LSPG_ENODEV, "no CUDA device: %s", cudaGetErrorString(e));
+    if (device >= count) return fail(LSPG_ENODEV, "device %d out of range (%d devices)", device, count);
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+      return fail(LSPG_ENODEV, "device %d is sm_%d%d; this library contains sm_100a code only (no fallback)", device,
+                  prop.major, prop.minor);
+    h->num_sms = prop.multiProcessorCount;
+    CUDA_TRY(cudaSetDevice(device));
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CUDA_TRY(cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &fn, 12000, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail(LSPG_ECUDA, "cuTensorMapEncodeTiled not available");
+    h->encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  int rc = build_network(h.get());
+  if (rc) return rc;
+  *out = h.release();
+  return LSPG_OK;
+}
+
+int lspg_destroy(lspg_handle h) {
+  if (!h) return LSPG_OK;
+  if (h->device >= 0) {
+    cudaSetDevice(h->device);
+    for (auto& L : h->layers) {
+      if (L.d_w) cudaFree(L.d_w);
+      if (L.d_scale) cudaFree(L.d_scale);
+      if (L.d_shift) cudaFree(L.d_shift);
+    }
+  }
+  delete h;
+  return LSPG_OK;
+}
+
+int lspg_load_weights(lspg_handle h, const lspg_tensor* tensors, int n) {
+  if (!h || (!tensors && n > 0)) return fail(LSPG_EINVAL, "null argument");
+  if (h->device >= 0) CUDA_TRY(cudaSetDevice(h->device));
+  std::map<std::string, const lspg_tensor*> by_name;
+  for (int i = 0; i < n; ++i) {
+    if (!tensors[i].name || !tensors[i].data) return fail(LSPG_EINVAL, "tensor %d has a null name or data pointer", i);
+    std::string nm = tensors[i].name;
+    if (nm.rfind("module.", 0) == 0) nm = nm.substr(7);   // DataParallel prefix (base_model.py:213-215)
+    by_name[nm] = &tensors[i];
+  }
+  auto take = [&](const std::string& key, std::vector<float>& dst, size_t expect, bool* changed) -> int {
+    auto it = by_name.find(key);
+    if (it == by_name.end()) return LSPG_OK;   // strict=False
+    if (static_cast<size_t>(it->second->numel) != expect)
+      return fail(LSPG_EINVAL, "%s has %lld elements, expected %zu", key.c_str(), static_cast<long long>(it->second->numel), expect);
+    dst.assign(it->second->data, it->second->data + expect);
+    *changed = true;
+    return LSPG_OK;
+  };
+  for (auto& L : h->layers) {
+    const int cin_total = (L.kind == K_HEAD) ? h->in_nc : (L.cin[0] + (L.n_src == 2 ? L.cin[1] : 0));
+    const size_t wn = static_cast<size_t>(L.cout) * cin_total * 9;
+    bool changed = false;
+    int rc;
+    if (L.w.empty()) { L.w.assign(wn, 0.0f); changed = true; }
+    if ((rc = take(L.conv_key + ".weight", L.w, wn, &changed))) return rc;
+    if (L.has_bn) {
+      if (L.bn_w.empty()) { L.bn_w.assign(L.cout, 1.f); L.bn_b.assign(L.cout, 0.f); L.bn_m.assign(L.cout, 0.f); L.bn_v.assign(L.cout, 1.f); }
+      if ((rc = take(L.bn_key + ".weight", L.bn_w, L.cout, &changed))) return rc;
+      if ((rc = take(L.bn_key + ".bias", L.bn_b, L.cout, &changed))) return rc;
+      if ((rc = take(L.bn_key + ".running_mean", L.bn_m, L.cout, &changed))) return rc;
+      if ((rc = take(L.bn_key + ".running_var", L.bn_v, L.cout, &changed))) return rc;
+    }
+    if (changed || L.dirty) {
+      pack_layer(h, L);
+      if ((rc = upload_layer(h, L))) return rc;
+      L.dirty = false;
+    }
+  }
+  h->weights_loaded = true;
+  return LSPG_OK;
+}
+
+int lspg_workspace_bytes(lspg_handle h, int batch, int height, int width, int mode, size_t* out) {
+  if (!h || !out) return fail(LSPG_EINVAL, "null argument");
+  int rc = check_shape(h, batch, height, width, mode);
+  if (rc) return rc;
+  *out = workspace_bytes(h, batch, height, width, mode);
+  return LSPG_OK;
+}
+
+int lspg_forward(lspg_handle h, const float* feature_map, int64_t fm_bstride, const float* cand, int64_t cand_bstride,
+                 float* out, int batch, int height, int width, void* workspace, size_t workspace_bytes_in, int mode,
+                 void* stream) {
+  if (!h) return fail(LSPG_EINVAL, "null handle");
+  if (h->device < 0) return fail(LSPG_ENODEV, "host-only handle: lspg_forward needs an sm_100 device (no CPU path exists)");
+  if (!h->weights_loaded) return fail(LSPG_ESTATE, "lspg_load_weights has not been called");
+  if (!feature_map || !out || !workspace || (h->in_nc > 1 && !cand)) return fail(LSPG_EINVAL, "null buffer");
+  int rc = check_shape(h, batch, height, width, mode);
+  if (rc) return rc;
+  const size_t need = workspace_bytes(h, batch, height, width, mode);
+  if (workspace_bytes_in < need) return fail(LSPG_ESTATE, "workspace too small: %zu < %zu", workspace_bytes_in, need);
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const auto key = std::make_tuple(batch, height, width, mode, workspace);
+  auto it = h->plans.find(key);
+  if (it == h->plans.end()) {
+    std::unique_ptr<Plan> P(new Plan);
+    if ((rc = build_plan(h, P.get(), batch, height, width, mode, workspace))) return rc;
+    if (h->plans.size() > 16) h->plans.clear();
+    it = h->plans.emplace(key, std::move(P)).first;
+  }
+  Plan* P = it->second.get();
+  h->last_plan = P;
+  const int NL = nl_of(mode);
+  const bool debug_sync = getenv("LSPG_DEBUG_SYNC") != nullptr;   // per-layer sync + error attribution (bring-up)
+  // 1. input packer (cat + NCHW->NHWC + bf16 + space-to-depth)
+  {
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(static_cast<uint8_t*>(workspace) + P->tensor_off[0]);
+    const long long limb_stride = static_cast<long long>(P->tensor_limb_stride[0] / 2);
+    const long long total = static_cast<long long>(batch) * (height / 2) * (width / 2);
+    int blocks = static_cast<int>((total + 127) / 128);
+    if (blocks > h->num_sms * 16) blocks = h->num_sms * 16;
+    if (NL == 1)
+      pack_input_s2d_kernel<1><<<blocks, 128, 0, st>>>(feature_map, fm_bstride, cand, cand_bstride, h->in_nc, dst, limb_stride, batch, height, width);
+    else
+      pack_input_s2d_kernel<2><<<blocks, 128, 0, st>>>(feature_map, fm_bstride, cand, cand_bstride, h->in_nc, dst, limb_stride, batch, height, width);
+    CUDA_TRY(cudaGetLastError());
+    if (debug_sync) CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  // 2. conv stack
+  for (size_t i = 0; i < h->layers.size(); ++i) {
+    PlanLayer& pl = P->layers[i];
+    if (h->layers[i].kind == K_TAIL) pl.prm.out_f32 = out;
+    if ((rc = launch_layer(pl, h->layers[i].kind, NL, st))) return rc;
+    if (debug_sync) {
+      cudaError_t e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess)
+        return fail(LSPG_ECUDA, "layer %zu (kind %d, %s, bn %d, grid %d, tiles %d) failed: %s", i, h->layers[i].kind,
+                    h->layers[i].conv_key.c_str(), pl.bn, pl.grid, pl.prm.total_tiles, cudaGetErrorString(e));
+    }
+  }
+  return LSPG_OK;
+}
+
+// ---------------------------------------------------------------------------------------- introspection
+int lspg_num_layers(lspg_handle h, int* out) {
+  if (!h || !out) return fail(LSPG_EINVAL, "null argument");
+  *out = static_cast<int>(h->layers.size());
+  return LSPG_OK;
+}
+
+int lspg_layer_info_get(lspg_handle h, int layer, lspg_layer_info* o) {
+  if (!h || !o) return fail(LSPG_EINVAL, "null argument");
+  if (layer < 0 || layer >= static_cast<int>(h->layers.size())) return fail(LSPG_EINVAL, "layer %d out of range", layer);
+  const Layer& L = h->layers[layer];
+  memset(o, 0, sizeof(*o));
+  o->kind = L.kind; o->n_src = L.n_src;
+  for (int s = 0; s < 2; ++s) { o->src[s] = L.src[s]; o->cin[s] = L.cin[s]; }
+  o->out = L.out; o->res = L.res; o->cout = L.cout; o->cout_pad = L.cout_pad;
+  o->n_phases = L.n_phases; o->n_taps = L.n_taps; o->k_total = L.k_total; o->relu = L.relu; o->has_bn = L.has_bn;
+  memcpy(o->tap_map, L.tap_map, sizeof(o->tap_map));
+  memcpy(o->tap_dx, L.tap_dx, sizeof(o->tap_dx));
+  memcpy(o->tap_dy, L.tap_dy, sizeof(o->tap_dy));
+  snprintf(o->conv_key, sizeof(o->conv_key), "%s", L.conv_key.c_str());
+  snprintf(o->bn_key, sizeof(o->bn_key), "%s", L.bn_key.c_str());
+  return LSPG_OK;
+}
+
+int lspg_layer_packed(lspg_handle h, int layer, int limb, uint16_t* dst, int64_t count) {
+  if (!h || !dst) return fail(LSPG_EINVAL, "null argument");
+  if (layer < 0 || layer >= static_cast<int>(h->layers.size()) || limb < 0 || limb > 1) return fail(LSPG_EINVAL, "bad layer/limb");
+  const Layer& L = h->layers[layer];
+  if (L.packed[limb].empty()) return fail(LSPG_ESTATE, "weights not loaded");
+  if (static_cast<size_t>(count) != L.packed[limb].size()) return fail(LSPG_EINVAL, "count %lld != %zu", static_cast<long long>(count), L.packed[limb].size());
+  memcpy(dst, L.packed[limb].data(), L.packed[limb].size() * 2);
+  return LSPG_OK;
+}
+
+int lspg_layer_affine(lspg_handle h, int layer, float* scale, float* shift, int64_t count) {
+  if (!h || !scale || !shift) return fail(LSPG_EINVAL, "null argument");
+  if (layer < 0 || layer >= static_cast<int>(h->layers.size())) return fail(LSPG_EINVAL, "bad layer");
+  const Layer& L = h->layers[layer];
+  if (L.scale.empty()) return fail(LSPG_ESTATE, "weights not loaded");
+  if (count != L.cout_pad) return fail(LSPG_EINVAL, "count %lld != %d", static_cast<long long>(count), L.cout_pad);
+  memcpy(scale, L.scale.data(), L.cout_pad * 4);
+  memcpy(shift, L.shift.data(), L.cout_pad * 4);
+  return LSPG_OK;
+}
+
+int lspg_num_tensors(lspg_handle h, int* out) {
+  if (!h || !out) return fail(LSPG_EINVAL, "null argument");
+  *out = static_cast<int>(h->tensors.size());
+  return LSPG_OK;
+}
+
+int lspg_tensor_shape(lspg_handle h, int id, int height, int width, int* c, int* th, int* tw) {
+  if (!h || !c || !th || !tw) return fail(LSPG_EINVAL, "null argument");
+  if (id < 0 || id >= static_cast<int>(h->tensors.size())) return fail(LSPG_EINVAL, "tensor %d out of range", id);
+  *c = h->tensors[id].channels; *th = height >> h->tensors[id].shift; *tw = width >> h->tensors[id].shift;
+  return LSPG_OK;
+}
+
+int lspg_debug_read_tensor(lspg_handle h, int id, int limb, uint16_t* dst, int64_t count) {
+  if (!h || !dst) return fail(LSPG_EINVAL, "null argument");
+  if (h->device < 0 || !h->last_plan) return fail(LSPG_ESTATE, "no forward has run on this handle");
+  Plan* P = h->last_plan;
+  if (id < 0 || id >= static_cast<int>(h->tensors.size())) return fail(LSPG_EINVAL, "tensor %d out of range", id);
+  if (limb < 0 || limb >= nl_of(P->mode)) return fail(LSPG_EINVAL, "limb %d not present in this mode", limb);
+  const size_t bytes = tensor_bytes_one_limb(h->tensors[id], P->batch, P->height, P->width);
+  if (static_cast<size_t>(count) * 2 != bytes) return fail(LSPG_EINVAL, "count %lld != %zu", static_cast<long long>(count), bytes / 2);
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpy(dst, static_cast<uint8_t*>(P->workspace) + P->tensor_off[id] + limb * P->tensor_limb_stride[id], bytes,
+                      cudaMemcpyDeviceToHost));
+  return LSPG_OK;
+}
+
+int lspg_launches_per_forward(lspg_handle h, int* out) {
+  if (!h || !out) return fail(LSPG_EINVAL, "null argument");
+  *out = 1 + static_cast<int>(h->layers.size());
+  return LSPG_OK;
+}
+
+int lspg_flops_per_frame(lspg_handle h, int height, int width, double* out) {
+  if (!h || !out) return fail(LSPG_EINVAL, "null argument");
+  double total = 0;
+  for (const auto& L : h->layers) {
+    // algorithmic work of the REFERENCE conv this layer implements: 2 * Ho*Wo*Cout*Cin*9
+    const int cin_total = (L.kind == K_HEAD) ? h->in_nc : (L.cin[0] + (L.n_src == 2 ? L.cin[1] : 0));
+    int oshift = L.grid_shift;                                   // output grid
+    if (L.kind == K_UP || L.kind == K_TAIL) oshift = L.grid_shift - 1;   // upsampled output
+    total += 2.0 * (height >> oshift) * (width >> oshift) * static_cast<double>(L.cout) * cin_total * 9.0;
+  }
+  *out = total;
+  return LSPG_OK;
+}
+
+}  // extern "C"

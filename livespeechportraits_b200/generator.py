@@ -1,0 +1,243 @@
+"""Drop-in replacement for the reference's ``models/feature2face_G.py:Feature2Face_G``.
+
+Same constructor (``Feature2Face_G(opt)``, reads ``opt.size / ngf / n_downsample_G / fp16 / isTrain``,
+reference lines 8-21), same ``state_dict`` key grammar (``netG.model.model.<i>...``, so
+``BaseModel.load_networks`` - models/base_model.py:193-223 - works unchanged, with or without the
+DataParallel ``module.`` prefix), same ``forward(input[B,13,H,W] fp32) -> [B,3,H,W] fp32`` contract
+(lines 27-34) and the same behaviour under ``networks.init_net`` (models/networks.py:382-402: ``.to(gpu)``,
+optional ``DataParallel`` wrap, ``init_weights`` finds real ``Conv2d``/``BatchNorm2d`` leaves).
+
+The module tree only HOLDS parameters.  ``forward`` never runs a torch op on them: it hands device pointers
+to the C-ABI library (include/lspg.h), which runs the hand-written sm_100a kernels on the current CUDA stream.
+There is no CPU or eager fallback: a CPU input, a non-Blackwell device or a missing library raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+KIND_HEAD, KIND_S1, KIND_S2, KIND_UP, KIND_TAIL = range(5)
+
+
+class _Holder(nn.Module):
+    """Anonymous container node of the parameter tree (stands where nn.Sequential / blocks stand upstream)."""
+
+    def forward(self, *a, **k):  # pragma: no cover - never called
+        raise RuntimeError("parameter holder; the generator runs through liblspg")
+
+
+def _default_mode(opt) -> str:
+    env = os.environ.get("LSP_B200_PRECISION")
+    if env:
+        if env not in _lib.LSPG_MODE:
+            raise ValueError(f"LSP_B200_PRECISION must be one of {sorted(_lib.LSPG_MODE)}")
+        return env
+    # opt.fp16 (reference: torch.cuda.amp.autocast, feature2face_G.py:28-30) = caller accepts reduced precision
+    return "fast" if getattr(opt, "fp16", 0) else "parity"
+
+
+class Feature2Face_G(nn.Module):
+    def __init__(self, opt, precision: Optional[str] = None):
+        super().__init__()
+        self.opt = opt
+        self.isTrain = getattr(opt, "isTrain", False)
+        size = getattr(opt, "size", "normal")
+        if size not in _lib.LSPG_VARIANT:
+            raise NotImplementedError(
+                f"opt.size={size!r}: only 'normal' and 'large' are built for B200 (the 'small' U-Net takes a 23-channel "
+                "input that no shipped config produces)")
+        self.variant = size
+        self.ngf = int(getattr(opt, "ngf", 64))
+        self.num_downs = int(getattr(opt, "n_downsample_G", 8))
+        self.in_nc, self.out_nc = 13, 3                      # feature2face_G.py:18-21
+        self.precision = precision or _default_mode(opt)
+        self._lib = _lib.load()
+        self._handle = C.c_void_p()
+        self._device_index: Optional[int] = None
+        self._weights_dirty = True
+        self._workspaces: Dict[Tuple[int, int, int, int, int], torch.Tensor] = {}
+        # host-only handle: gives the layer list (keys, shapes) without needing a GPU
+        plan = C.c_void_p()
+        _lib.check(self._lib.lspg_create(C.byref(plan), _lib.LSPG_VARIANT[size], self.ngf, self.num_downs, self.in_nc,
+                                         self.out_nc, -1))
+        try:
+            self._build_parameter_tree(plan)
+        finally:
+            self._lib.lspg_destroy(plan)
+
+    # ------------------------------------------------------------------ parameter tree
+    def _build_parameter_tree(self, plan) -> None:
+        n = C.c_int()
+        _lib.check(self._lib.lspg_num_layers(plan, C.byref(n)))
+        info = _lib.LspgLayerInfo()
+        for i in range(n.value):
+            _lib.check(self._lib.lspg_layer_info_get(plan, i, C.byref(info)))
+            cin = self.in_nc if info.kind == KIND_HEAD else info.cin[0] + (info.cin[1] if info.n_src == 2 else 0)
+            stride = 2 if info.kind in (KIND_HEAD, KIND_S2) else 1
+            self._attach(info.conv_key.decode(), nn.Conv2d(cin, info.cout, 3, stride, 1, bias=False))
+            if info.has_bn:
+                self._attach(info.bn_key.decode(), nn.BatchNorm2d(info.cout))
+
+    def _attach(self, dotted: str, leaf: nn.Module) -> None:
+        node: nn.Module = self
+        parts = dotted.split(".")
+        for p in parts[:-1]:
+            if p not in node._modules:
+                node.add_module(p, _Holder())
+            node = node._modules[p]
+        node.add_module(parts[-1], leaf)
+
+    # ------------------------------------------------------------------ weight tracking
+    def mark_weights_dirty(self) -> None:
+        """Call after editing parameters in place; load_state_dict/.to()/.eval() do it automatically."""
+        self._weights_dirty = True
+
+    def load_state_dict(self, state_dict, strict: bool = True, **kw):
+        out = super().load_state_dict(state_dict, strict=strict, **kw)
+        self._weights_dirty = True
+        return out
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        self._weights_dirty = True
+        return out
+
+    def train(self, mode: bool = True):
+        self._weights_dirty = True
+        return super().train(mode)
+
+    def _ensure_handle(self, device: torch.device) -> None:
+        if device.type != "cuda":
+            raise RuntimeError("livespeechportraits_b200 has no CPU path: inputs must live on a B200 (sm_100) device")
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        if self._handle and self._device_index == idx:
+            return
+        if self._handle:
+            self._lib.lspg_destroy(self._handle)
+            self._handle = C.c_void_p()
+        h = C.c_void_p()
+        _lib.check(self._lib.lspg_create(C.byref(h), _lib.LSPG_VARIANT[self.variant], self.ngf, self.num_downs, self.in_nc,
+                                         self.out_nc, idx))
+        self._handle, self._device_index = h, idx
+        self._weights_dirty = True
+        self._workspaces.clear()
+
+    def _push_weights(self) -> None:
+        sd = super().state_dict()
+        names: List[bytes] = []
+        keep: List[torch.Tensor] = []
+        for k, v in sd.items():
+            if k.endswith("num_batches_tracked"):
+                continue
+            names.append(k.encode())
+            keep.append(v.detach().to(device="cpu", dtype=torch.float32).contiguous())
+        arr = (_lib.LspgTensor * len(keep))()
+        for i, (nm, t) in enumerate(zip(names, keep)):
+            arr[i].name = nm
+            arr[i].data = C.cast(t.data_ptr(), C.POINTER(C.c_float))
+            arr[i].numel = t.numel()
+        _lib.check(self._lib.lspg_load_weights(self._handle, arr, len(keep)))
+        self._weights_dirty = False
+
+    # ------------------------------------------------------------------ forward
+    def _workspace(self, batch: int, height: int, width: int, mode: int) -> torch.Tensor:
+        key = (batch, height, width, mode, self._device_index)
+        ws = self._workspaces.get(key)
+        if ws is None:
+            need = C.c_size_t()
+            _lib.check(self._lib.lspg_workspace_bytes(self._handle, batch, height, width, mode, C.byref(need)))
+            ws = torch.empty(need.value, dtype=torch.uint8, device=torch.device("cuda", self._device_index))
+            if len(self._workspaces) >= 4:
+                self._workspaces.clear()
+            self._workspaces[key] = ws
+        return ws
+
+    def render(self, feature_map: torch.Tensor, cand_image: Optional[torch.Tensor], out: Optional[torch.Tensor] = None,
+               precision: Optional[str] = None) -> torch.Tensor:
+        """Fused ``torch.cat([feature_map, cand_image], 1)`` + generator (feature2face_model.py:231-233).
+
+        ``cand_image`` may have batch 1 (broadcast over the frames, as demo.py:266 reuses one candidate set).
+        """
+        if self.training:
+            raise NotImplementedError("training-mode BatchNorm is not implemented: call .eval() (inference path only)")
+        if feature_map.dtype != torch.float32 or (cand_image is not None and cand_image.dtype != torch.float32):
+            raise TypeError("inputs must be fp32 (reference contract)")
+        self._ensure_handle(feature_map.device)
+        if self._weights_dirty:
+            self._push_weights()
+        if cand_image is None:
+            if feature_map.dim() != 4 or feature_map.shape[1] != self.in_nc:
+                raise ValueError(f"expected [B,{self.in_nc},H,W] input, got {tuple(feature_map.shape)}")
+            x = feature_map.contiguous()
+            b, _, h, w = x.shape
+            fm_ptr, fm_stride = x.data_ptr(), self.in_nc * h * w
+            cand_ptr, cand_stride = x.data_ptr() + 4 * h * w, self.in_nc * h * w
+            hold = (x,)
+        else:
+            fm = feature_map.contiguous()
+            cd = cand_image.contiguous()
+            b, c1, h, w = fm.shape
+            if c1 != 1 or cd.shape[1] != self.in_nc - 1 or cd.shape[2:] != fm.shape[2:] or cd.shape[0] not in (1, b):
+                raise ValueError(f"expected [B,1,H,W] + [B|1,{self.in_nc - 1},H,W], got {tuple(fm.shape)} + {tuple(cd.shape)}")
+            if cd.device != fm.device:
+                raise ValueError("feature_map and cand_image must be on the same device")
+            fm_ptr, fm_stride = fm.data_ptr(), h * w
+            cand_ptr, cand_stride = cd.data_ptr(), (0 if cd.shape[0] == 1 and b > 1 else (self.in_nc - 1) * h * w)
+            hold = (fm, cd)
+        mode = _lib.LSPG_MODE[precision or self.precision]
+        ws = self._workspace(b, h, w, mode)
+        if out is None:
+            out = torch.empty((b, self.out_nc, h, w), dtype=torch.float32, device=feature_map.device)
+        elif out.shape != (b, self.out_nc, h, w) or out.dtype != torch.float32 or not out.is_contiguous():
+            raise ValueError("out must be a contiguous fp32 [B,3,H,W] tensor")
+        stream = torch.cuda.current_stream(feature_map.device).cuda_stream
+        _lib.check(self._lib.lspg_forward(self._handle, fm_ptr, fm_stride, cand_ptr, cand_stride, out.data_ptr(), b, h, w,
+                                          ws.data_ptr(), ws.numel(), mode, stream))
+        del hold
+        return out
+
+    def forward(self, input: torch.Tensor) -> torch.Tensor:  # noqa: A002 - reference argument name
+        return self.render(input, None)
+
+    # ------------------------------------------------------------------ introspection used by tests / bench
+    def launches_per_forward(self) -> int:
+        n = C.c_int()
+        _lib.check(self._lib.lspg_launches_per_forward(self._handle, C.byref(n)))
+        return n.value
+
+    def flops_per_frame(self, height: int, width: int) -> float:
+        v = C.c_double()
+        _lib.check(self._lib.lspg_flops_per_frame(self._handle, height, width, C.byref(v)))
+        return v.value
+
+    def debug_read_tensor(self, tensor_id: int, batch: int, height: int, width: int, limb: int = 0) -> torch.Tensor:
+        c, th, tw = C.c_int(), C.c_int(), C.c_int()
+        _lib.check(self._lib.lspg_tensor_shape(self._handle, tensor_id, height, width, C.byref(c), C.byref(th), C.byref(tw)))
+        buf = torch.empty((batch, th.value, tw.value, c.value), dtype=torch.bfloat16)
+        _lib.check(self._lib.lspg_debug_read_tensor(self._handle, tensor_id, limb, buf.data_ptr(), buf.numel()))
+        return buf
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None):
+                self._lib.lspg_destroy(self._handle)
+        except Exception:
+            pass
+
+
+def install(models_module_name: str = "models.feature2face_G") -> None:
+    """Swap the reference's generator class for this one; ``demo.py`` then runs unchanged.
+
+    ``models/feature2face_model.py:27`` resolves ``feature2face_G.Feature2Face_G`` at call time, so replacing the
+    module attribute before ``create_model(opt)`` is enough.
+    """
+    import importlib
+
+    mod = importlib.import_module(models_module_name)
+    mod.Feature2Face_G = Feature2Face_G
