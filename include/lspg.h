@@ -111,6 +111,12 @@ int lspg_tensor_shape(lspg_handle h, int id, int height, int width, int* c, int*
 int lspg_debug_read_tensor(lspg_handle h, int id, int limb, uint16_t* dst, int64_t count);
 /* Kernels one lspg_forward call launches (for bench.py's gpu_launches accounting). */
 int lspg_launches_per_forward(lspg_handle h, int* out);
+/* Per-launch timing: when enabled, every lspg_forward records a CUDA event on `stream` before its first
+ * kernel and after each kernel (no host synchronisation).  lspg_profile_read synchronises on the recorded
+ * events, returns the average duration in milliseconds of each of the launches_per_forward launches over the
+ * forwards recorded since the previous read (at most 256 are kept), and resets the record. */
+int lspg_profile_enable(lspg_handle h, int enabled);
+int lspg_profile_read(lspg_handle h, float* avg_ms, int count, int* n_forwards);
 /* Algorithmic conv FLOPs per frame (2*MAC of the reference convs) at height x width. */
 int lspg_flops_per_frame(lspg_handle h, int height, int width, double* out);
 

@@ -118,6 +118,9 @@ struct lspg_ctx {
   EncodeTiledFn encode = nullptr;
   std::map<std::tuple<int, int, int, int, void*>, std::unique_ptr<Plan>> plans;
   Plan* last_plan = nullptr;
+  bool profiling = false;
+  std::vector<std::vector<cudaEvent_t>> prof_events;   // one event set per recorded forward
+  size_t prof_used = 0;
 };
 
 namespace {
@@ -641,6 +644,8 @@ int lspg_destroy(lspg_handle h) {
       if (L.d_scale) cudaFree(L.d_scale);
       if (L.d_shift) cudaFree(L.d_shift);
     }
+    for (auto& set : h->prof_events)
+      for (auto& e : set) cudaEventDestroy(e);
   }
   delete h;
   return LSPG_OK;
@@ -661,6 +666,7 @@ int lspg_load_weights(lspg_handle h, const lspg_tensor* tensors, int n) {
     if (it == by_name.end()) return LSPG_OK;   // strict=False
     if (static_cast<size_t>(it->second->numel) != expect)
       return fail(LSPG_EINVAL, "%s has %lld elements, expected %zu", key.c_str(), static_cast<long long>(it->second->numel), expect);
+    if (dst.size() == expect && memcmp(dst.data(), it->second->data, expect * sizeof(float)) == 0) return LSPG_OK;
     dst.assign(it->second->data, it->second->data + expect);
     *changed = true;
     return LSPG_OK;
@@ -722,6 +728,16 @@ int lspg_forward(lspg_handle h, const float* feature_map, int64_t fm_bstride, co
   h->last_plan = P;
   const int NL = nl_of(mode);
   const bool debug_sync = getenv("LSPG_DEBUG_SYNC") != nullptr;   // per-layer sync + error attribution (bring-up)
+  std::vector<cudaEvent_t>* evs = nullptr;
+  if (h->profiling && h->prof_used < 256) {
+    if (h->prof_used == h->prof_events.size()) {
+      std::vector<cudaEvent_t> set(h->layers.size() + 2);
+      for (auto& e : set) CUDA_TRY(cudaEventCreate(&e));
+      h->prof_events.push_back(set);
+    }
+    evs = &h->prof_events[h->prof_used++];
+    CUDA_TRY(cudaEventRecord((*evs)[0], st));
+  }
   // 1. input packer (cat + NCHW->NHWC + bf16 + space-to-depth)
   {
     __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(static_cast<uint8_t*>(workspace) + P->tensor_off[0]);
@@ -735,12 +751,14 @@ int lspg_forward(lspg_handle h, const float* feature_map, int64_t fm_bstride, co
       pack_input_s2d_kernel<2><<<blocks, 128, 0, st>>>(feature_map, fm_bstride, cand, cand_bstride, h->in_nc, dst, limb_stride, batch, height, width);
     CUDA_TRY(cudaGetLastError());
     if (debug_sync) CUDA_TRY(cudaStreamSynchronize(st));
+    if (evs) CUDA_TRY(cudaEventRecord((*evs)[1], st));
   }
   // 2. conv stack
   for (size_t i = 0; i < h->layers.size(); ++i) {
     PlanLayer& pl = P->layers[i];
     if (h->layers[i].kind == K_TAIL) pl.prm.out_f32 = out;
     if ((rc = launch_layer(pl, h->layers[i].kind, NL, st))) return rc;
+    if (evs) CUDA_TRY(cudaEventRecord((*evs)[i + 2], st));
     if (debug_sync) {
       cudaError_t e = cudaStreamSynchronize(st);
       if (e != cudaSuccess)
@@ -827,6 +845,36 @@ int lspg_debug_read_tensor(lspg_handle h, int id, int limb, uint16_t* dst, int64
 int lspg_launches_per_forward(lspg_handle h, int* out) {
   if (!h || !out) return fail(LSPG_EINVAL, "null argument");
   *out = 1 + static_cast<int>(h->layers.size());
+  return LSPG_OK;
+}
+
+int lspg_profile_enable(lspg_handle h, int enabled) {
+  if (!h) return fail(LSPG_EINVAL, "null handle");
+  if (h->device < 0) return fail(LSPG_ENODEV, "host-only handle");
+  h->profiling = enabled != 0;
+  h->prof_used = 0;
+  return LSPG_OK;
+}
+
+int lspg_profile_read(lspg_handle h, float* avg_ms, int count, int* n_forwards) {
+  if (!h || !avg_ms || !n_forwards) return fail(LSPG_EINVAL, "null argument");
+  const int n = 1 + static_cast<int>(h->layers.size());
+  if (count != n) return fail(LSPG_EINVAL, "count %d != launches per forward %d", count, n);
+  CUDA_TRY(cudaSetDevice(h->device));
+  for (int i = 0; i < n; ++i) avg_ms[i] = 0.f;
+  for (size_t f = 0; f < h->prof_used; ++f) {
+    auto& set = h->prof_events[f];
+    CUDA_TRY(cudaEventSynchronize(set[n]));
+    for (int i = 0; i < n; ++i) {
+      float ms = 0.f;
+      CUDA_TRY(cudaEventElapsedTime(&ms, set[i], set[i + 1]));
+      avg_ms[i] += ms;
+    }
+  }
+  *n_forwards = static_cast<int>(h->prof_used);
+  if (h->prof_used)
+    for (int i = 0; i < n; ++i) avg_ms[i] /= static_cast<float>(h->prof_used);
+  h->prof_used = 0;
   return LSPG_OK;
 }
 

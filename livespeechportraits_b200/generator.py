@@ -103,6 +103,12 @@ class Feature2Face_G(nn.Module):
         self._weights_dirty = True
         return out
 
+    def _load_from_state_dict(self, *a, **k):
+        # reached for every module of the tree when ANY ancestor's load_state_dict runs (e.g. the
+        # nn.DataParallel wrapper networks.init_net creates, whose load never calls the override above)
+        self._weights_dirty = True
+        return super()._load_from_state_dict(*a, **k)
+
     def _apply(self, fn, *a, **k):
         out = super()._apply(fn, *a, **k)
         self._weights_dirty = True
@@ -215,6 +221,38 @@ class Feature2Face_G(nn.Module):
         v = C.c_double()
         _lib.check(self._lib.lspg_flops_per_frame(self._handle, height, width, C.byref(v)))
         return v.value
+
+    def profile_enable(self, enabled: bool = True) -> None:
+        """Record CUDA events around every kernel of subsequent forwards (lspg_profile_enable)."""
+        _lib.check(self._lib.lspg_profile_enable(self._handle, 1 if enabled else 0))
+
+    def profile_read(self) -> Tuple[List[float], int]:
+        """(average ms per launch [input packer, conv 0, conv 1, ...], forwards averaged); resets the record."""
+        n = self.launches_per_forward()
+        buf = (C.c_float * n)()
+        cnt = C.c_int()
+        _lib.check(self._lib.lspg_profile_read(self._handle, buf, n, C.byref(cnt)))
+        return list(buf), cnt.value
+
+    def layer_table(self, height: int, width: int) -> List[dict]:
+        """One dict per conv launch: kind, state-dict key, channels, output grid and algorithmic FLOPs per frame."""
+        n = C.c_int()
+        _lib.check(self._lib.lspg_num_layers(self._handle, C.byref(n)))
+        rows = []
+        info = _lib.LspgLayerInfo()
+        for i in range(n.value):
+            _lib.check(self._lib.lspg_layer_info_get(self._handle, i, C.byref(info)))
+            cin = self.in_nc if info.kind == KIND_HEAD else info.cin[0] + (info.cin[1] if info.n_src == 2 else 0)
+            if info.out >= 0:
+                c, th, tw = C.c_int(), C.c_int(), C.c_int()
+                _lib.check(self._lib.lspg_tensor_shape(self._handle, info.out, height, width, C.byref(c), C.byref(th), C.byref(tw)))
+                oh, ow = th.value, tw.value
+            else:
+                oh, ow = height, width
+            rows.append(dict(kind=info.kind, key=info.conv_key.decode(), cin=cin, cout=info.cout, out_h=oh, out_w=ow,
+                             flops=2.0 * oh * ow * info.cout * cin * 9, src=[info.src[0], info.src[1]][: info.n_src],
+                             out=info.out, res=info.res))
+        return rows
 
     def debug_read_tensor(self, tensor_id: int, batch: int, height: int, width: int, limb: int = 0) -> torch.Tensor:
         c, th, tw = C.c_int(), C.c_int(), C.c_int()

@@ -1,0 +1,176 @@
+"""Host-side logic, CPU only: the C ABI loads and exports what include/lspg.h declares, error behaviour,
+the drop-in module's state-dict contract, and the launch plan (structure, packing, BatchNorm folding, tap
+geometry) executed by the CPU plan emulator against the oracle.  No GPU compute here."""
+import ctypes as C
+import os
+import re
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from livespeechportraits_b200 import _lib
+from livespeechportraits_b200.generator import Feature2Face_G
+from oracle import f2f_oracle as O
+import plan_emulator as E
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def opt(size="normal", **kw):
+    d = dict(isTrain=False, size=size, n_downsample_G=8, ngf=64, fp16=0)
+    d.update(kw)
+    return types.SimpleNamespace(**d)
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "lspg.h")).read()
+    declared = set(re.findall(r"^(?:int|const char\*)\s+(lspg_\w+)\s*\(", header, flags=re.M))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    for name in declared:
+        assert getattr(lib, name) is not None
+
+
+def test_create_argument_errors_and_no_cpu_path():
+    lib = _lib.load()
+    h = C.c_void_p()
+    assert lib.lspg_create(C.byref(h), 7, 64, 8, 13, 3, -1) == -1          # LSPG_EINVAL
+    assert b"variant" in lib.lspg_last_error()
+    assert lib.lspg_create(C.byref(h), 0, 48, 8, 13, 3, -1) == -1
+    assert lib.lspg_create(C.byref(h), 0, 64, 8, 13, 4, -1) == -1
+    if not torch.cuda.is_available():
+        assert lib.lspg_create(C.byref(h), 0, 64, 8, 13, 3, 0) == -2        # LSPG_ENODEV: no device, no fallback
+    assert lib.lspg_create(C.byref(h), 0, 64, 8, 13, 3, -1) == 0
+    buf = (C.c_float * 4)()
+    rc = lib.lspg_forward(h, buf, 0, buf, 0, buf, 1, 256, 256, buf, 16, 0, None)
+    assert rc == -2 and b"no CPU path" in lib.lspg_last_error()
+    need = C.c_size_t()
+    assert lib.lspg_workspace_bytes(h, 1, 300, 256, 0, C.byref(need)) == -1  # H must be a multiple of 256
+    assert lib.lspg_workspace_bytes(h, 1, 256, 256, 5, C.byref(need)) == -1  # unknown mode
+    assert lib.lspg_workspace_bytes(h, 2, 512, 512, 1, C.byref(need)) == 0 and need.value > 0
+    lib.lspg_destroy(h)
+
+
+def test_load_weights_validation_and_module_prefix():
+    lib = _lib.load()
+    h = C.c_void_p()
+    assert lib.lspg_create(C.byref(h), 0, 64, 8, 13, 3, -1) == 0
+    w = torch.randn(64, 13, 3, 3)
+    arr = (_lib.LspgTensor * 1)()
+    arr[0].name = b"module.netG.model.model.0.weight"               # DataParallel prefix is accepted
+    arr[0].data = C.cast(w.data_ptr(), C.POINTER(C.c_float))
+    arr[0].numel = w.numel()
+    assert lib.lspg_load_weights(h, arr, 1) == 0
+    arr[0].numel = w.numel() - 1
+    assert lib.lspg_load_weights(h, arr, 1) == -1
+    assert b"elements" in lib.lspg_last_error()
+    lib.lspg_destroy(h)
+
+
+@pytest.mark.parametrize("variant", ["normal", "large"])
+def test_module_state_dict_contract(variant):
+    net = Feature2Face_G(opt(variant))
+    spec = O.state_dict_spec(variant)
+    sd = net.state_dict()
+    assert list(sd.keys()) == list(spec.keys())
+    assert all(tuple(sd[k].shape) == tuple(s) for k, (r, s) in spec.items())
+    res = net.load_state_dict(O.make_state_dict(variant, "B"), strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    # the reference's init_weights (networks.py:347-378) dispatches on class names: the leaves are real modules
+    names = {m.__class__.__name__ for m in net.modules()}
+    assert "Conv2d" in names and "BatchNorm2d" in names
+    n_conv = sum(1 for m in net.modules() if isinstance(m, torch.nn.Conv2d))
+    assert n_conv == (76 if variant == "large" else 46)
+
+
+def test_module_refuses_cpu_and_train_mode():
+    net = Feature2Face_G(opt("normal")).eval()
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        net(torch.zeros(1, 13, 256, 256))
+    net.train()
+    with pytest.raises(NotImplementedError):
+        net(torch.zeros(1, 13, 256, 256))
+    with pytest.raises(NotImplementedError):
+        Feature2Face_G(opt("small"))
+
+
+@pytest.mark.parametrize("variant,recipe", [("normal", "B"), ("large", "A")])
+def test_launch_plan_reproduces_the_oracle(variant, recipe):
+    sd = O.make_state_dict(variant, recipe)
+    plan = E.HostPlan(variant, sd)
+    try:
+        kinds = [L.kind for L in plan.layers]
+        assert kinds[0] == E.KIND_HEAD and kinds[-1] == E.KIND_TAIL
+        assert len(kinds) == (76 if variant == "large" else 46)
+        fm, cand = O.make_inputs(1, 256, 256)
+        x = torch.cat([fm, cand], 1)
+        ref = O.generator_forward(sd, x, variant)
+        out = E.run_plan(plan, x, limbs=2)
+        # hi+lo bf16 weights carry ~16 mantissa bits: the plan must reproduce the oracle to ~1e-4
+        assert (out - ref).abs().max().item() <= 2e-4
+        out_bf16 = E.run_plan(plan, x, limbs=1, round_act=lambda t: t.bfloat16().float())
+        assert (out_bf16 - ref).abs().max().item() <= 5e-2
+    finally:
+        plan.close()
+
+
+def test_bn_fold_matches_batchnorm_formula():
+    sd = O.make_state_dict("normal", "B")
+    plan = E.HostPlan("normal", sd)
+    try:
+        for i, L in enumerate(plan.layers):
+            s, b = plan.affine(i)
+            if L.has_bn:
+                key = L.bn_key.decode()
+                inv = 1.0 / torch.sqrt(sd[key + ".running_var"] + 1e-5)
+                assert torch.allclose(s[: L.cout], sd[key + ".weight"] * inv, rtol=1e-6, atol=1e-7)
+                assert torch.allclose(b[: L.cout], sd[key + ".bias"] - sd[key + ".running_mean"] * sd[key + ".weight"] * inv,
+                                      rtol=1e-5, atol=1e-6)
+            else:
+                assert float((s - 1).abs().max()) == 0 and float(b.abs().max()) == 0
+    finally:
+        plan.close()
+
+
+def test_flops_accounting_matches_oracle():
+    lib = _lib.load()
+    for variant in ("normal", "large"):
+        h = C.c_void_p()
+        assert lib.lspg_create(C.byref(h), _lib.LSPG_VARIANT[variant], 64, 8, 13, 3, -1) == 0
+        v = C.c_double()
+        assert lib.lspg_flops_per_frame(h, 512, 512, C.byref(v)) == 0
+        assert int(v.value) == O.conv_flops_per_frame(variant, 512, 512)
+        lib.lspg_destroy(h)
+
+
+@pytest.mark.skipif(not O.reference_available(), reason="reference checkout not present on this machine")
+def test_drop_in_through_the_reference_model_class(tmp_path):
+    """create_model -> Feature2FaceModel -> our generator; load_networks round-trips a 'module.'-prefixed pkl."""
+    import contextlib
+    import io
+    import sys
+    O.reference_generator("normal")            # puts the reference on sys.path
+    from livespeechportraits_b200 import generator as G
+    import models.feature2face_G as ref_mod  # type: ignore
+    original = ref_mod.Feature2Face_G
+    try:
+        G.install()
+        sd = O.make_state_dict("normal", "B")
+        ckpt = tmp_path / "Feature2Face.pkl"
+        torch.save({"module." + k: v for k, v in sd.items()}, ckpt)
+        o = O.reference_opt("normal", load_epoch=str(ckpt), checkpoints_dir=str(tmp_path))
+        with contextlib.redirect_stdout(io.StringIO()):
+            from models import create_model  # type: ignore
+            model = create_model(o)
+            model.setup(o)
+            model.eval()
+        g = model.Feature2Face_G
+        assert isinstance(g, G.Feature2Face_G) and not g.training
+        got = g.state_dict()
+        assert all(torch.equal(got[k], v) for k, v in sd.items())
+        with pytest.raises(RuntimeError, match="no CPU path"):
+            model.inference(torch.zeros(1, 1, 256, 256), torch.zeros(1, 12, 256, 256))
+    finally:
+        ref_mod.Feature2Face_G = original
