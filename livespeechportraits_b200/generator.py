@@ -212,14 +212,25 @@ class Feature2Face_G(nn.Module):
         return self.render(input, None)
 
     # ------------------------------------------------------------------ introspection used by tests / bench
+    def _info_handle(self):
+        """Device handle if one exists, else a host-only handle (structure queries need no GPU)."""
+        if self._handle:
+            return self._handle
+        if not getattr(self, "_host_handle", None):
+            h = C.c_void_p()
+            _lib.check(self._lib.lspg_create(C.byref(h), _lib.LSPG_VARIANT[self.variant], self.ngf, self.num_downs,
+                                             self.in_nc, self.out_nc, -1))
+            self._host_handle = h
+        return self._host_handle
+
     def launches_per_forward(self) -> int:
         n = C.c_int()
-        _lib.check(self._lib.lspg_launches_per_forward(self._handle, C.byref(n)))
+        _lib.check(self._lib.lspg_launches_per_forward(self._info_handle(), C.byref(n)))
         return n.value
 
     def flops_per_frame(self, height: int, width: int) -> float:
         v = C.c_double()
-        _lib.check(self._lib.lspg_flops_per_frame(self._handle, height, width, C.byref(v)))
+        _lib.check(self._lib.lspg_flops_per_frame(self._info_handle(), height, width, C.byref(v)))
         return v.value
 
     def profile_enable(self, enabled: bool = True) -> None:
@@ -236,16 +247,17 @@ class Feature2Face_G(nn.Module):
 
     def layer_table(self, height: int, width: int) -> List[dict]:
         """One dict per conv launch: kind, state-dict key, channels, output grid and algorithmic FLOPs per frame."""
+        hdl = self._info_handle()
         n = C.c_int()
-        _lib.check(self._lib.lspg_num_layers(self._handle, C.byref(n)))
+        _lib.check(self._lib.lspg_num_layers(hdl, C.byref(n)))
         rows = []
         info = _lib.LspgLayerInfo()
         for i in range(n.value):
-            _lib.check(self._lib.lspg_layer_info_get(self._handle, i, C.byref(info)))
+            _lib.check(self._lib.lspg_layer_info_get(hdl, i, C.byref(info)))
             cin = self.in_nc if info.kind == KIND_HEAD else info.cin[0] + (info.cin[1] if info.n_src == 2 else 0)
             if info.out >= 0:
                 c, th, tw = C.c_int(), C.c_int(), C.c_int()
-                _lib.check(self._lib.lspg_tensor_shape(self._handle, info.out, height, width, C.byref(c), C.byref(th), C.byref(tw)))
+                _lib.check(self._lib.lspg_tensor_shape(hdl, info.out, height, width, C.byref(c), C.byref(th), C.byref(tw)))
                 oh, ow = th.value, tw.value
             else:
                 oh, ow = height, width
@@ -265,6 +277,8 @@ class Feature2Face_G(nn.Module):
         try:
             if getattr(self, "_handle", None):
                 self._lib.lspg_destroy(self._handle)
+            if getattr(self, "_host_handle", None):
+                self._lib.lspg_destroy(self._host_handle)
         except Exception:
             pass
 
