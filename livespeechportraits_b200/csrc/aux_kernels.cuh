@@ -17,6 +17,9 @@ __global__ void pack_input_s2d_kernel(const float* __restrict__ fm, long long fm
                                       const float* __restrict__ cand, long long cand_bstride, int in_nc,
                                       __nv_bfloat16* __restrict__ dst, long long limb_stride, int batch, int height,
                                       int width) {
+  // PDL: the previous forward's kernels may still be reading the packed tensor this kernel overwrites
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int wo = width >> 1, ho = height >> 1;
   const long long total = static_cast<long long>(batch) * ho * wo;
   const long long plane = static_cast<long long>(height) * width;

@@ -40,10 +40,12 @@ struct alignas(64) ConvParams {
   CUtensorMap a[4];          // activation views: [parity or concat source], dims {C, X, Y, N, limb}
   CUtensorMap w;             // packed weights, dims {K, Cout_pad, limb*n_phases + phase}
   CUtensorMap out[4];        // output views per phase, dims {C, X, Y, N, limb}
-  CUtensorMap res;           // residual view
   const float* scale;        // folded BatchNorm (or 1/0), [Cout_pad]
   const float* shift;
   float* out_f32;            // tail only: fp32 NCHW [B, 3, 2*hs, 2*ws]
+  const __nv_bfloat16* res_ptr;   // residual tensor (NHWC, same grid as the output), limb 0; read directly by the epilogue
+  long long res_limb_stride;      // elements between limbs
+  int32_t res_channels;
   uint32_t idesc;            // UMMA instruction descriptor (M=128, N=BN, bf16 x bf16 -> f32, K-major)
   int32_t n_taps, n_src;
   int32_t chunks[2];         // 64-channel chunks per concat source
@@ -57,6 +59,19 @@ struct alignas(64) ConvParams {
   int8_t tap_map[4][kMaxTaps];   // [phase][tap] -> index into a[] (added to the concat source index)
   int8_t tap_dx[4][kMaxTaps];
   int8_t tap_dy[4][kMaxTaps];
+  // patch mode (conv_patch_kernel): one halo patch {64 ch, patch_w, patch_h} per (tile, source, chunk) whose origin
+  // is the tile origin + (patch_dx0, patch_dy0)[phase]; every tap is a row offset inside the patch.
+  int32_t patch_w, patch_h;
+  int8_t patch_dx0[4], patch_dy0[4];
+  int16_t tap_row[4][kMaxTaps];  // [phase][tap] -> first patch row of the tap's shifted A tile
+  int32_t desc_base_offset;      // 1: set the UMMA descriptor base-offset field from the start address (bring-up switch)
+  // split-K: the K loop (v1: K blocks; patch mode: (source, chunk) items) is cut into n_split ranges of split_len;
+  // tile index = split * tiles_per_split + tile.  Each CTA writes its raw fp32 accumulator tile to
+  // partial[tile_index][128][BN]; splitk_reduce_kernel sums the splits and applies the epilogue.
+  int32_t n_split, split_len, tiles_per_split;
+  float* partial;
+  int32_t tap_rotate;            // patch mode: tile (x,y) dependent rotation of the tap order, so that concurrently
+                                 // running CTAs do not all request the same weight tile from L2 at the same time
 };
 
 template <int BN, int NL, bool TAIL>
@@ -77,12 +92,14 @@ struct ConvCfg {
 };
 
 struct TileCoord {
-  int z, nt, x0, y0, n0;
+  int z, nt, x0, y0, n0, split;
 };
 
 __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int t) {
   TileCoord c;
   const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
+  c.split = t / p.tiles_per_split;
+  t -= c.split * p.tiles_per_split;
   int mt = t % m_tiles;
   int r = t / m_tiles;
   c.nt = r % p.n_tiles;
@@ -104,127 +121,21 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
 
-template <int BN, int NL, bool TAIL>
-__global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_constant__ ConvParams p) {
-  using Cfg = ConvCfg<BN, NL, TAIL>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* stg_base = smem + Cfg::kStages * Cfg::kStage;
-  uint8_t* aux = stg_base + Cfg::kStgBytes;
-  float* s_scale = reinterpret_cast<float*>(aux);
-  float* s_shift = s_scale + BN;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(aux + 2 * BN * 4);
-  uint64_t* full_bar = bars;                       // [kStages]
-  uint64_t* empty_bar = bars + Cfg::kStages;       // [kStages]
-  uint64_t* tfull_bar = bars + 2 * Cfg::kStages;   // [2]
-  uint64_t* tempty_bar = tfull_bar + 2;            // [2]
-  uint64_t* stg_bar = tempty_bar + 2;              // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stg_bar + 2);
 
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
+template <int NSTG>
+struct StgCfg {
+  static constexpr int kNumStg = NSTG;
+};
 
-  if (warp == 0 && lane == 0) {
-    for (int i = 0; i < 4; ++i) ptx::prefetch_tmap(&p.a[i]);
-    ptx::prefetch_tmap(&p.w);
-    if (!TAIL) {
-      for (int i = 0; i < 4; ++i) ptx::prefetch_tmap(&p.out[i]);
-      ptx::prefetch_tmap(&p.res);
-    }
-    for (int i = 0; i < Cfg::kStages; ++i) {
-      ptx::mbar_init(&full_bar[i], 1);
-      ptx::mbar_init(&empty_bar[i], 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      ptx::mbar_init(&tfull_bar[i], 1);
-      ptx::mbar_init(&tempty_bar[i], 4);   // one arrive per epilogue warp
-      ptx::mbar_init(&stg_bar[i], 1);
-    }
-    ptx::fence_mbar_init();
-  }
-  if (warp == 1) {
-    ptx::tmem_alloc(tmem_slot, Cfg::kTmemCols);
-    ptx::tmem_relinquish();
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  int kb_per_tap = 0;
-  for (int s = 0; s < p.n_src; ++s) kb_per_tap += p.chunks[s];
-  const int num_kb = p.n_taps * kb_per_tap;
-
-  if (warp == 0) {
-    // ===================================================================== TMA producer
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-      const TileCoord tc = decode_tile(p, t);
-      int kb = 0;
-      for (int tap = 0; tap < p.n_taps; ++tap) {
-        const int amap = p.tap_map[tc.z][tap];
-        const int xx = tc.x0 + p.tap_dx[tc.z][tap];
-        const int yy = tc.y0 + p.tap_dy[tc.z][tap];
-        for (int s = 0; s < p.n_src; ++s) {
-          for (int c = 0; c < p.chunks[s]; ++c, ++kb) {
-            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-            if (lane == 0) {
-              uint8_t* st = smem + stage * Cfg::kStage;
-              ptx::mbar_expect_tx(&full_bar[stage], Cfg::kStage);
-#pragma unroll
-              for (int l = 0; l < NL; ++l) {
-                ptx::tma_load_5d(&p.a[amap + s], &full_bar[stage], st + l * kATile, c * kChunk, xx, yy, tc.n0, l);
-                ptx::tma_load_3d(&p.w, &full_bar[stage], st + NL * kATile + l * Cfg::kBTile, kb * kChunk, tc.nt * BN,
-                                 l * p.n_phases + tc.z);
-              }
-            }
-            __syncwarp();
-            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================================================================== MMA issuer
-    int stage = 0;
-    uint32_t phase = 0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-      ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-      ptx::tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * BN;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        ptx::mbar_wait(&full_bar[stage], phase);
-        ptx::tc_fence_after();
-        if (lane == 0) {
-          const uint32_t a0 = ptx::smem_u32(smem + stage * Cfg::kStage);
-          const uint32_t b0 = a0 + NL * kATile;
-          const uint64_t a_hi = ptx::umma_desc_sw128(a0);
-          const uint64_t b_hi = ptx::umma_desc_sw128(b0);
-#pragma unroll
-          for (int k = 0; k < kChunk / 16; ++k) {
-            const uint32_t accum = (kb > 0 || k > 0) ? 1u : 0u;
-            // +32 bytes along K inside the 128-byte swizzle row = +2 in descriptor address units
-            ptx::umma_f16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, p.idesc, accum);
-            if (NL == 2) {
-              const uint64_t a_lo = ptx::umma_desc_sw128(a0 + kATile);
-              const uint64_t b_lo = ptx::umma_desc_sw128(b0 + Cfg::kBTile);
-              ptx::umma_f16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, p.idesc, 1u);
-              ptx::umma_f16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, p.idesc, 1u);
-            }
-          }
-          ptx::umma_commit(&empty_bar[stage]);                 // smem slot reusable once these MMAs retire
-          if (kb == num_kb - 1) ptx::umma_commit(&tfull_bar[acc]);   // accumulator complete
-        }
-        __syncwarp();
-        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
-      }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-    }
-  } else {
+// Epilogue role (warps 2..5, 128 threads): drains the TMEM accumulators of every tile this CTA owns.
+// NSTG = number of residual-in / result-out staging buffers behind `stg_base`.
+template <int BN, int NL, bool TAIL, int NSTG>
+__device__ __forceinline__ void epilogue_warps(const ConvParams& p, uint8_t* stg_base, float* s_scale, float* s_shift,
+                                               uint64_t* tfull_bar, uint64_t* tempty_bar, uint64_t* stg_bar,
+                                               uint32_t tmem_base, int warp, int lane) {
+  using Cfg = StgCfg<NSTG>;
     // ===================================================================== epilogue (warps 2..5)
+    ptx::pdl_wait();   // residual reads, output / split-K partial writes must not overtake the previous kernel
     const int q = warp & 3;                     // TMEM lane quarter this warp may read
     const int row = q * 32 + lane;              // tile row = pixel index inside the tile
     const int etid = threadIdx.x - 64;          // 0..127
@@ -233,24 +144,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     uint32_t acc_phase = 0;
     uint32_t g = 0;                             // running staging-chunk counter (selects buffer + parity)
 
-    // The leader "prepares" staging buffer g % kNumStg for chunk g: waits until the TMA store that last read
-    // it has drained, then either TMA-loads the residual chunk into it or simply releases it.
-    auto prepare = [&](uint32_t gg, const TileCoord& tc, int chunk) {
-      if (TAIL) return;
-      const int j = gg % (Cfg::kNumStg > 0 ? Cfg::kNumStg : 1);
-      uint8_t* buf = stg_base + j * NL * kATile;
-      if (p.has_res) {
-        ptx::mbar_expect_tx(&stg_bar[j], NL * kATile);
-#pragma unroll
-        for (int l = 0; l < NL; ++l)
-          ptx::tma_load_5d(&p.res, &stg_bar[j], buf + l * kATile, tc.nt * BN + chunk * kChunk, tc.x0, tc.y0, tc.n0, l);
-      } else {
-        ptx::mbar_arrive(&stg_bar[j]);
-      }
-    };
-
     constexpr int kChunksPerTile = TAIL ? 1 : BN / kChunk;
-    bool first = true;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
       const TileCoord tc = decode_tile(p, t);
       // folded BatchNorm parameters of this tile's channel range
@@ -258,8 +152,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
         s_scale[i] = p.scale[tc.nt * BN + i];
         s_shift[i] = p.shift[tc.nt * BN + i];
       }
-      if (!TAIL && Cfg::kNumStg == 2 && first && leader) prepare(g, tc, 0);
-      first = false;
+      const bool split_mode = !TAIL && p.n_split > 1;
       ptx::named_bar_sync(1, kEpiThreads);
 
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
@@ -294,87 +187,98 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
             }
           }
         }
+      } else if constexpr (!TAIL) {
+       if (split_mode) {
+        // ---- split-K partial: raw fp32 accumulator rows -> partial[t][row][BN]; the reduce kernel finishes the job
+        float* dst = p.partial + (static_cast<size_t>(t) * kTileM + row) * BN;
+#pragma unroll 1
+        for (int c32 = 0; c32 < BN / 32; ++c32) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32(t_acc + c32 * 32, v);
+          ptx::tmem_ld_wait();
+          if (c32 == BN / 32 - 1) {
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            *reinterpret_cast<uint4*>(dst + c32 * 32 + e * 4) = make_uint4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+        }
       } else {
+        // ---- regular: scale/shift (+ residual, read straight from global: this thread's own pixel row) + ReLU,
+        //      bf16 (hi, lo) into a swizzled staging tile, TMA store.  kNumStg staging buffers rotate; the only wait
+        //      on a previous store sits right before the smem writes, after the TMEM loads and the math.
+        const int tw_ = row & ((1 << p.tw_log2) - 1);
+        const int th_ = (row >> p.tw_log2) & ((1 << p.th_log2) - 1);
+        const int nb_ = row >> (p.tw_log2 + p.th_log2);
+        const int pn = tc.n0 + nb_, py_ = tc.y0 + th_, px_ = tc.x0 + tw_;
+        const bool pix_ok = pn < p.batch && py_ < p.hs && px_ < p.ws;
+        const __nv_bfloat16* res_row = p.res_ptr + ((static_cast<size_t>(pn) * p.hs + py_) * p.ws + px_) * p.res_channels +
+                                       tc.nt * BN;
         for (int chunk = 0; chunk < kChunksPerTile; ++chunk, ++g) {
           const int j = g % Cfg::kNumStg;
-          const uint32_t par = (g / Cfg::kNumStg) & 1;
           uint8_t* buf = stg_base + j * NL * kATile;
-          if (leader) {
-            // all earlier stores must have finished READING their staging buffer before it is refilled
-            ptx::tma_store_wait_read<0>();
-            if (Cfg::kNumStg == 2) {
-              // prefetch the next chunk's residual into the other buffer (its last store has drained)
-              int nchunk = chunk + 1;
-              int nt_tile = t;
-              if (nchunk == kChunksPerTile) { nchunk = 0; nt_tile = t + gridDim.x; }
-              if (nt_tile < p.total_tiles) {
-                const TileCoord ntc = (nt_tile == t) ? tc : decode_tile(p, nt_tile);
-                prepare(g + 1, ntc, nchunk);
-              }
-            } else {
-              prepare(g, tc, chunk);
-            }
-          }
-          ptx::mbar_wait(&stg_bar[j], par);
-
           uint8_t* my_row = buf + row * 128;
+          uint4 rs[NL][8];                                   // residual: 64 channels x NL limbs of this pixel
+          if (p.has_res) {
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            uint32_t v[32];
-            ptx::tmem_ld_32x32(t_acc + chunk * kChunk + half * 32, v);
-            ptx::tmem_ld_wait();
-            if (chunk == kChunksPerTile - 1 && half == 1) {
-              // accumulator fully drained into registers: hand the TMEM buffer back to the MMA warp
-              ptx::tc_fence_before();
-              __syncwarp();
-              if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+            for (int l = 0; l < NL; ++l)
+#pragma unroll
+              for (int c16 = 0; c16 < 8; ++c16)
+                rs[l][c16] = pix_ok ? __ldg(reinterpret_cast<const uint4*>(res_row + l * p.res_limb_stride + chunk * kChunk) + c16)
+                                    : make_uint4(0u, 0u, 0u, 0u);
+          }
+          uint32_t vv[2][32];
+          ptx::tmem_ld_32x32(t_acc + chunk * kChunk, vv[0]);
+          ptx::tmem_ld_32x32(t_acc + chunk * kChunk + 32, vv[1]);
+          ptx::tmem_ld_wait();
+          if (chunk == kChunksPerTile - 1) {
+            // accumulator fully drained into registers: hand the TMEM buffer back to the MMA warp
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+          }
+          // staging buffer j is free once the store issued kNumStg chunks ago has finished reading it
+          if (leader) ptx::tma_store_wait_read<Cfg::kNumStg - 1>();
+          ptx::named_bar_sync(3, kEpiThreads);
+#pragma unroll
+          for (int piece = 0; piece < 8; ++piece) {          // 16-byte pieces: 8 channels each
+            const int phys = (piece ^ (row & 7)) << 4;       // 128B swizzle
+            float y[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int ch = chunk * kChunk + piece * 8 + e;
+              y[e] = fmaf(__uint_as_float(vv[piece >> 2][(piece & 3) * 8 + e]), s_scale[ch], s_shift[ch]);
             }
+            if (p.has_res) {
 #pragma unroll
-            for (int c16 = 0; c16 < 4; ++c16) {            // 16-byte pieces: 8 channels each
-              const int piece = half * 4 + c16;            // logical 16B chunk index inside the 128B row
-              const int phys = (piece ^ (row & 7)) << 4;   // 128B swizzle
-              float y[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const int ch = chunk * kChunk + piece * 8 + e;
-                y[e] = fmaf(__uint_as_float(v[c16 * 8 + e]), s_scale[ch], s_shift[ch]);
-              }
-              if (p.has_res) {
-                const uint4 r = *reinterpret_cast<const uint4*>(my_row + phys);
-                const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+              for (int l = 0; l < NL; ++l) {
+                const uint32_t rr[4] = {rs[l][piece].x, rs[l][piece].y, rs[l][piece].z, rs[l][piece].w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   y[2 * e] += bf16_lo(rr[e]);
                   y[2 * e + 1] += bf16_hi(rr[e]);
                 }
-                if (NL == 2) {
-                  const uint4 r2 = *reinterpret_cast<const uint4*>(my_row + kATile + phys);
-                  const uint32_t rr2[4] = {r2.x, r2.y, r2.z, r2.w};
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    y[2 * e] += bf16_lo(rr2[e]);
-                    y[2 * e + 1] += bf16_hi(rr2[e]);
-                  }
-                }
               }
-              if (p.relu) {
+            }
+            if (p.relu) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) y[e] = fmaxf(y[e], 0.0f);
-              }
-              uint4 o;
-              o.x = pack_bf16x2(y[0], y[1]);
-              o.y = pack_bf16x2(y[2], y[3]);
-              o.z = pack_bf16x2(y[4], y[5]);
-              o.w = pack_bf16x2(y[6], y[7]);
-              *reinterpret_cast<uint4*>(my_row + phys) = o;
-              if (NL == 2) {
-                const uint32_t oo[4] = {o.x, o.y, o.z, o.w};
-                uint32_t lo[4];
+              for (int e = 0; e < 8; ++e) y[e] = fmaxf(y[e], 0.0f);
+            }
+            uint4 o;
+            o.x = pack_bf16x2(y[0], y[1]);
+            o.y = pack_bf16x2(y[2], y[3]);
+            o.z = pack_bf16x2(y[4], y[5]);
+            o.w = pack_bf16x2(y[6], y[7]);
+            *reinterpret_cast<uint4*>(my_row + phys) = o;
+            if (NL == 2) {
+              const uint32_t oo[4] = {o.x, o.y, o.z, o.w};
+              uint32_t lo[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e)
-                  lo[e] = pack_bf16x2(y[2 * e] - bf16_lo(oo[e]), y[2 * e + 1] - bf16_hi(oo[e]));
-                *reinterpret_cast<uint4*>(my_row + kATile + phys) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-              }
+              for (int e = 0; e < 4; ++e)
+                lo[e] = pack_bf16x2(y[2 * e] - bf16_lo(oo[e]), y[2 * e + 1] - bf16_hi(oo[e]));
+              *reinterpret_cast<uint4*>(my_row + kATile + phys) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             }
           }
           ptx::fence_proxy_async_smem();
@@ -386,10 +290,139 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
             ptx::tma_store_commit();
           }
         }
+       }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (!TAIL && leader) ptx::tma_store_wait_all<0>();   // global writes complete before the CTA retires
+}
+
+template <int BN, int NL, bool TAIL>
+__global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_constant__ ConvParams p) {
+  using Cfg = ConvCfg<BN, NL, TAIL>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stg_base = smem + Cfg::kStages * Cfg::kStage;
+  uint8_t* aux = stg_base + Cfg::kStgBytes;
+  float* s_scale = reinterpret_cast<float*>(aux);
+  float* s_shift = s_scale + BN;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(aux + 2 * BN * 4);
+  uint64_t* full_bar = bars;                       // [kStages]
+  uint64_t* empty_bar = bars + Cfg::kStages;       // [kStages]
+  uint64_t* tfull_bar = bars + 2 * Cfg::kStages;   // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;            // [2]
+  uint64_t* stg_bar = tempty_bar + 2;              // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stg_bar + 2);
+
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);   // provably warp-uniform
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 4; ++i) ptx::prefetch_tmap(&p.a[i]);
+    ptx::prefetch_tmap(&p.w);
+    if (!TAIL) {
+      for (int i = 0; i < 4; ++i) ptx::prefetch_tmap(&p.out[i]);
+    }
+    for (int i = 0; i < Cfg::kStages; ++i) {
+      ptx::mbar_init(&full_bar[i], 1);
+      ptx::mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&tfull_bar[i], 1);
+      ptx::mbar_init(&tempty_bar[i], 4);   // one arrive per epilogue warp
+      ptx::mbar_init(&stg_bar[i], 1);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  ptx::pdl_launch_dependents();   // the next kernel may start its prologue; it waits (pdl_wait) before touching our output
+
+  int kb_per_tap = 0;
+  for (int s = 0; s < p.n_src; ++s) kb_per_tap += p.chunks[s];
+  const int num_kb = p.n_taps * kb_per_tap;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    ptx::pdl_wait();                // activations are written by the previous kernel
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      const TileCoord tc = decode_tile(p, t);
+      const int kb0 = tc.split * p.split_len;
+      const int kb1 = (kb0 + p.split_len < num_kb) ? kb0 + p.split_len : num_kb;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        const int tap = kb / kb_per_tap;
+        const int rem = kb - tap * kb_per_tap;
+        const int s = (rem < p.chunks[0]) ? 0 : 1;
+        const int c = s ? rem - p.chunks[0] : rem;
+        const int amap = p.tap_map[tc.z][tap];
+        const int xx = tc.x0 + p.tap_dx[tc.z][tap];
+        const int yy = tc.y0 + p.tap_dy[tc.z][tap];
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (ptx::elect_one()) {
+          uint8_t* st = smem + stage * Cfg::kStage;
+          ptx::mbar_expect_tx(&full_bar[stage], Cfg::kStage);
+#pragma unroll
+          for (int l = 0; l < NL; ++l) {
+            ptx::tma_load_5d(&p.a[amap + s], &full_bar[stage], st + l * kATile, c * kChunk, xx, yy, tc.n0, l);
+            ptx::tma_load_3d(&p.w, &full_bar[stage], st + NL * kATile + l * Cfg::kBTile, kb * kChunk, tc.nt * BN,
+                             l * p.n_phases + tc.z);
+          }
+        }
+        __syncwarp();
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      const TileCoord tc = decode_tile(p, t);
+      const int kb0 = tc.split * p.split_len;
+      const int kb1 = (kb0 + p.split_len < num_kb) ? kb0 + p.split_len : num_kb;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        ptx::mbar_wait(&full_bar[stage], phase);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const uint32_t a0 = ptx::smem_u32(smem + stage * Cfg::kStage);
+          const uint32_t b0 = a0 + NL * kATile;
+          const uint64_t a_hi = ptx::umma_desc_sw128(a0);
+          const uint64_t b_hi = ptx::umma_desc_sw128(b0);
+#pragma unroll
+          for (int k = 0; k < kChunk / 16; ++k) {
+            const uint32_t accum = (kb > kb0 || k > 0) ? 1u : 0u;
+            // +32 bytes along K inside the 128-byte swizzle row = +2 in descriptor address units
+            ptx::umma_f16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, p.idesc, accum);
+            if (NL == 2) {
+              const uint64_t a_lo = ptx::umma_desc_sw128(a0 + kATile);
+              const uint64_t b_lo = ptx::umma_desc_sw128(b0 + Cfg::kBTile);
+              ptx::umma_f16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, p.idesc, 1u);
+              ptx::umma_f16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, p.idesc, 1u);
+            }
+          }
+          ptx::umma_commit(&empty_bar[stage]);                 // smem slot reusable once these MMAs retire
+          if (kb == kb1 - 1) ptx::umma_commit(&tfull_bar[acc]);   // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    epilogue_warps<BN, NL, TAIL, Cfg::kNumStg>(p, stg_base, s_scale, s_shift, tfull_bar, tempty_bar, stg_bar, tmem_base, warp, lane);
   }
 
   ptx::tc_fence_before();
@@ -397,6 +430,330 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+
+// ====================================================================================================
+// Patch mode.  The v1 kernel above re-loads a 16 KB A tile for every tap, i.e. reads the layer input 9x from
+// L2; ncu shows it pinned at the ~10.6 TB/s L2->SM limit with the tensor pipe 35-65 % busy
+// (profiles/r01_v1_ncu_full_first14_convs.md).  Here ONE halo patch {64 ch, TW+halo, TH+halo} is loaded per
+// (tile, source, 64-channel chunk) and all taps are addressed inside it: with TW = 8 an 8-row UMMA group is
+// one image row of the patch, so the shifted A tile of tap (dx,dy) is the same swizzled buffer described by
+//   start = patch + ((dy-dy0)*PW + (dx-dx0)) * 128 B,   stride between 8-row groups (SBO) = PW * 128 B.
+// The swizzle phase of a row is a function of its absolute smem address for both TMA and UMMA, so rows that
+// TMA wrote are read back consistently at any 128-byte-aligned start (descriptor base offset = (start>>7)&7).
+// A and B move through separate mbarrier rings: an A patch is consumed by n_taps B tiles.
+// ====================================================================================================
+constexpr int kPatchSlot = 23 * 1024 + 512;     // >= 10*18*128 bytes, multiple of 512; slots are 1024-aligned via kPatchStride
+constexpr int kPatchStride = 24 * 1024;
+
+template <int BN, int NL, bool TAIL>
+struct PatchCfg {
+  static constexpr int kBTile = BN * 128;
+  // taps per B stage: one mbarrier round trip per stage costs the MMA-issuing thread a few hundred cycles, so a
+  // stage must carry enough tensor work (>= ~500 cycles): 2 taps for N=128 bf16, 2-3 for N=64, all 9 for the tail.
+  static constexpr int kTPS = TAIL ? 9 : (BN >= 128 ? (NL == 1 ? 2 : 1) : (NL == 1 ? 3 : 2));
+  static constexpr int kAStage = NL * kPatchStride;
+  static constexpr int kBStage = NL * kTPS * kBTile;
+  static constexpr int kAStages = (NL == 1) ? 3 : 2;
+  static constexpr int kNumStg = TAIL ? 0 : (NL == 1 ? 2 : 1);
+  static constexpr int kStgBytes = kNumStg * NL * kATile;
+  static constexpr int kAux = 2048;
+  static constexpr int kAvail = kSmemBudget - 1024 - kStgBytes - kAux - kAStages * kAStage;
+  static constexpr int kBStagesRaw = kAvail / kBStage;
+  static constexpr int kBStages = kBStagesRaw > 8 ? 8 : kBStagesRaw;
+  static constexpr int kSmemBytes = 1024 + kAStages * kAStage + kBStages * kBStage + kStgBytes + kAux;
+  static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
+  static_assert(kBStages >= 2, "B ring needs at least two stages");
+  static_assert(2 * BN * 4 + (2 * 8 + 2 * 3 + 8) * 8 <= kAux, "aux region too small");
+};
+
+__device__ __forceinline__ uint64_t umma_desc_sw128_strided(uint32_t smem_addr, uint32_t sbo_bytes, bool base_off) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  if (base_off) d |= static_cast<uint64_t>((smem_addr >> 7) & 7u) << 49;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+template <int BN, int NL, bool TAIL>
+__global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_constant__ ConvParams p) {
+  using Cfg = PatchCfg<BN, NL, TAIL>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a_ring = smem;
+  uint8_t* b_ring = a_ring + Cfg::kAStages * Cfg::kAStage;
+  uint8_t* stg_base = b_ring + Cfg::kBStages * Cfg::kBStage;
+  uint8_t* aux = stg_base + Cfg::kStgBytes;
+  float* s_scale = reinterpret_cast<float*>(aux);
+  float* s_shift = s_scale + BN;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(aux + 2 * BN * 4);
+  uint64_t* afull_bar = bars;                               // [kAStages]
+  uint64_t* aempty_bar = afull_bar + Cfg::kAStages;         // [kAStages]
+  uint64_t* bfull_bar = aempty_bar + Cfg::kAStages;         // [kBStages]
+  uint64_t* bempty_bar = bfull_bar + Cfg::kBStages;         // [kBStages]
+  uint64_t* tfull_bar = bempty_bar + Cfg::kBStages;         // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;                     // [2]
+  uint64_t* stg_bar = tempty_bar + 2;                       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stg_bar + 2);
+
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);   // provably warp-uniform
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 4; ++i) ptx::prefetch_tmap(&p.a[i]);
+    ptx::prefetch_tmap(&p.w);
+    if (!TAIL) {
+      for (int i = 0; i < 4; ++i) ptx::prefetch_tmap(&p.out[i]);
+    }
+    for (int i = 0; i < Cfg::kAStages; ++i) { ptx::mbar_init(&afull_bar[i], 1); ptx::mbar_init(&aempty_bar[i], 1); }
+    for (int i = 0; i < Cfg::kBStages; ++i) { ptx::mbar_init(&bfull_bar[i], 1); ptx::mbar_init(&bempty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&tfull_bar[i], 1);
+      ptx::mbar_init(&tempty_bar[i], 4);
+      ptx::mbar_init(&stg_bar[i], 1);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  ptx::pdl_launch_dependents();   // the next kernel may start its prologue; it waits (pdl_wait) before touching our output
+
+  int kb_per_tap = 0;
+  for (int s = 0; s < p.n_src; ++s) kb_per_tap += p.chunks[s];   // = (source, chunk) items per tile
+  const int patch_bytes = p.patch_w * p.patch_h * 128;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    // Flat sequence of items (tile, concat-chunk ci).  The A patch of item j+1 is issued in the middle of item
+    // j's B tiles so that it is in flight while the MMA warp still works on item j.
+    ptx::pdl_wait();                // activations are written by the previous kernel
+    int ia = 0, ib = 0;
+    uint32_t pha = 0, phb = 0;
+    int a_tile = blockIdx.x, a_ci = -1;            // cursor of the next A patch to issue (-1: take the tile's first item)
+    auto issue_a = [&]() {
+      if (a_tile >= p.total_tiles) return;
+      const TileCoord tc = decode_tile(p, a_tile);
+      const int ci0 = tc.split * p.split_len;
+      const int ci1 = (ci0 + p.split_len < kb_per_tap) ? ci0 + p.split_len : kb_per_tap;
+      if (a_ci < 0) a_ci = ci0;
+      const int s = (a_ci < p.chunks[0]) ? 0 : 1;
+      const int c = (s == 0) ? a_ci : a_ci - p.chunks[0];
+      ptx::mbar_wait(&aempty_bar[ia], pha ^ 1);
+      if (ptx::elect_one()) {
+        ptx::mbar_expect_tx(&afull_bar[ia], NL * patch_bytes);
+#pragma unroll
+        for (int l = 0; l < NL; ++l)
+          ptx::tma_load_5d(&p.a[s], &afull_bar[ia], a_ring + ia * Cfg::kAStage + l * kPatchStride, c * kChunk,
+                           tc.x0 + p.patch_dx0[tc.z], tc.y0 + p.patch_dy0[tc.z], tc.n0, l);
+      }
+      __syncwarp();
+      if (++ia == Cfg::kAStages) { ia = 0; pha ^= 1; }
+      if (++a_ci == ci1) { a_ci = -1; a_tile += gridDim.x; }
+    };
+    issue_a();
+    const int n_groups = (p.n_taps + Cfg::kTPS - 1) / Cfg::kTPS;
+    const int a_after_group = (n_groups > 1) ? 1 : 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      const TileCoord tc = decode_tile(p, t);
+      const int ci0 = tc.split * p.split_len;
+      const int ci1 = (ci0 + p.split_len < kb_per_tap) ? ci0 + p.split_len : kb_per_tap;
+      for (int ci = ci0; ci < ci1; ++ci) {
+        for (int g = 0; g < n_groups; ++g) {
+          ptx::mbar_wait(&bempty_bar[ib], phb ^ 1);
+          if (ptx::elect_one()) {
+            uint8_t* st = b_ring + ib * Cfg::kBStage;
+            ptx::mbar_expect_tx(&bfull_bar[ib], Cfg::kBStage);
+#pragma unroll
+            for (int l = 0; l < NL; ++l)   // one box = kTPS taps x BN rows x 64 channels (taps beyond n_taps are zero-filled)
+              ptx::tma_load_4d(&p.w, &bfull_bar[ib], st + l * Cfg::kTPS * Cfg::kBTile, ci * kChunk, tc.nt * BN, g * Cfg::kTPS,
+                               l * p.n_phases + tc.z);
+          }
+          __syncwarp();
+          if (++ib == Cfg::kBStages) { ib = 0; phb ^= 1; }
+          if (g == a_after_group) issue_a();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    int ia = 0, ib = 0;
+    uint32_t pha = 0, phb = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const uint32_t sbo = static_cast<uint32_t>(p.patch_w) * 128u;
+    const bool boff = p.desc_base_offset != 0;
+    const int n_groups = (p.n_taps + Cfg::kTPS - 1) / Cfg::kTPS;
+    bool b_ready = false;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      const TileCoord tc = decode_tile(p, t);
+      ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      const int ci0 = tc.split * p.split_len;
+      const int ci1 = (ci0 + p.split_len < kb_per_tap) ? ci0 + p.split_len : kb_per_tap;
+      for (int ci = ci0; ci < ci1; ++ci) {
+        ptx::mbar_wait(&afull_bar[ia], pha);
+        const uint32_t a0 = ptx::smem_u32(a_ring + ia * Cfg::kAStage);
+        for (int g = 0; g < n_groups; ++g) {
+          if (!b_ready) ptx::mbar_wait(&bfull_bar[ib], phb);
+          ptx::tc_fence_after();
+          const int tap0 = g * Cfg::kTPS;
+          const int tap1 = (tap0 + Cfg::kTPS < p.n_taps) ? tap0 + Cfg::kTPS : p.n_taps;
+          if (ptx::elect_one()) {
+            const uint32_t b0 = ptx::smem_u32(b_ring + ib * Cfg::kBStage);
+            for (int tap = tap0; tap < tap1; ++tap) {
+              const uint32_t a_hi_addr = a0 + static_cast<uint32_t>(p.tap_row[tc.z][tap]) * 128u;
+              const uint32_t b_hi_addr = b0 + static_cast<uint32_t>(tap - tap0) * Cfg::kBTile;
+              const uint64_t a_hi = umma_desc_sw128_strided(a_hi_addr, sbo, boff);
+              const uint64_t b_hi = ptx::umma_desc_sw128(b_hi_addr);
+#pragma unroll
+              for (int k = 0; k < kChunk / 16; ++k) {
+                const uint32_t accum = (ci > ci0 || tap > 0 || k > 0) ? 1u : 0u;
+                ptx::umma_f16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, p.idesc, accum);
+                if (NL == 2) {
+                  const uint64_t a_lo = umma_desc_sw128_strided(a_hi_addr + kPatchStride, sbo, boff);
+                  const uint64_t b_lo = ptx::umma_desc_sw128(b_hi_addr + Cfg::kTPS * Cfg::kBTile);
+                  ptx::umma_f16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, p.idesc, 1u);
+                  ptx::umma_f16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, p.idesc, 1u);
+                }
+              }
+            }
+            ptx::umma_commit(&bempty_bar[ib]);
+            if (g == n_groups - 1) {
+              ptx::umma_commit(&aempty_bar[ia]);
+              if (ci == ci1 - 1) ptx::umma_commit(&tfull_bar[acc]);
+            }
+          }
+          __syncwarp();
+          if (++ib == Cfg::kBStages) { ib = 0; phb ^= 1; }
+          b_ready = ptx::mbar_try_wait(&bfull_bar[ib], phb);   // peek: overlaps the barrier round trip with the MMAs in flight
+        }
+        if (++ia == Cfg::kAStages) { ia = 0; pha ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    epilogue_warps<BN, NL, TAIL, Cfg::kNumStg>(p, stg_base, s_scale, s_shift, tfull_bar, tempty_bar, stg_bar, tmem_base, warp, lane);
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+
+// ====================================================================================================
+// Split-K finisher: out = epilogue( sum_s partial[s] ).  One thread = one pixel x 8 channels.
+// Memory-bound and tiny (the layers that use split-K have at most a few hundred output pixels per image).
+// ====================================================================================================
+struct ReduceParams {
+  const float* partial;
+  const float* scale;
+  const float* shift;
+  const __nv_bfloat16* res;
+  long long res_limb_stride;      // elements
+  __nv_bfloat16* out;
+  long long out_limb_stride;
+  int32_t n_split, tiles_per_split, m_tiles, n_tiles, n_phases;
+  int32_t tiles_x, tiles_y, tw_log2, th_log2, bn;
+  int32_t batch, hs, ws, up, channels, relu, has_res, nl;
+};
+
+__global__ void splitk_reduce_kernel(const ReduceParams p) {
+  ptx::pdl_wait();
+  ptx::pdl_launch_dependents();
+  const int groups = p.bn >> 3;
+  const long long total = static_cast<long long>(p.tiles_per_split) * kTileM * groups;
+  for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < total;
+       e += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(e % groups);
+    const long long r0 = e / groups;
+    const int row = static_cast<int>(r0 % kTileM);
+    const int tile = static_cast<int>(r0 / kTileM);
+    const int mt = tile % p.m_tiles;
+    const int r1 = tile / p.m_tiles;
+    const int nt = r1 % p.n_tiles;
+    const int z = r1 / p.n_tiles;
+    const int tx = mt % p.tiles_x;
+    const int r2 = mt / p.tiles_x;
+    const int ty = r2 % p.tiles_y;
+    const int tn = r2 / p.tiles_y;
+    const int tw = row & ((1 << p.tw_log2) - 1);
+    const int th = (row >> p.tw_log2) & ((1 << p.th_log2) - 1);
+    const int nb = row >> (p.tw_log2 + p.th_log2);
+    const int n = (tn << (7 - p.tw_log2 - p.th_log2)) + nb;
+    const int y = (ty << p.th_log2) + th, x = (tx << p.tw_log2) + tw;
+    if (n >= p.batch || y >= p.hs || x >= p.ws) continue;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    const size_t split_stride = static_cast<size_t>(p.tiles_per_split) * kTileM * p.bn;      // floats between splits
+    const float* src0 = p.partial + (static_cast<size_t>(tile) * kTileM + row) * p.bn + g * 8;
+    int s = 0;
+    for (; s + 4 <= p.n_split; s += 4) {       // four splits per trip: eight independent 16-byte loads in flight
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float4* src = reinterpret_cast<const float4*>(src0 + (s + u) * split_stride);
+        v[2 * u] = src[0];
+        v[2 * u + 1] = src[1];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {            // summation order stays s = 0, 1, 2, ... (deterministic)
+        acc[0] += v[2 * u].x; acc[1] += v[2 * u].y; acc[2] += v[2 * u].z; acc[3] += v[2 * u].w;
+        acc[4] += v[2 * u + 1].x; acc[5] += v[2 * u + 1].y; acc[6] += v[2 * u + 1].z; acc[7] += v[2 * u + 1].w;
+      }
+    }
+    for (; s < p.n_split; ++s) {
+      const float4* src = reinterpret_cast<const float4*>(src0 + s * split_stride);
+      const float4 a = src[0], b = src[1];
+      acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+      acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+    }
+    const int ch = nt * p.bn + g * 8;
+    const int oh = p.up ? 2 * p.hs : p.hs, ow = p.up ? 2 * p.ws : p.ws;
+    const int oy = p.up ? 2 * y + (z >> 1) : y, ox = p.up ? 2 * x + (z & 1) : x;
+    const size_t off = ((static_cast<size_t>(n) * oh + oy) * ow + ox) * p.channels + ch;
+    float yv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) yv[i] = fmaf(acc[i], p.scale[ch + i], p.shift[ch + i]);
+    if (p.has_res) {
+      for (int l = 0; l < p.nl; ++l) {
+        const uint4 r = *reinterpret_cast<const uint4*>(p.res + l * p.res_limb_stride + off);
+        const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { yv[2 * i] += bf16_lo(rr[i]); yv[2 * i + 1] += bf16_hi(rr[i]); }
+      }
+    }
+    if (p.relu) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) yv[i] = fmaxf(yv[i], 0.f);
+    }
+    uint4 o;
+    o.x = pack_bf16x2(yv[0], yv[1]); o.y = pack_bf16x2(yv[2], yv[3]);
+    o.z = pack_bf16x2(yv[4], yv[5]); o.w = pack_bf16x2(yv[6], yv[7]);
+    *reinterpret_cast<uint4*>(p.out + off) = o;
+    if (p.nl == 2) {
+      const uint32_t oo[4] = {o.x, o.y, o.z, o.w};
+      uint32_t lo[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) lo[i] = pack_bf16x2(yv[2 * i] - bf16_lo(oo[i]), yv[2 * i + 1] - bf16_hi(oo[i]));
+      *reinterpret_cast<uint4*>(p.out + p.out_limb_stride + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
   }
 }
 

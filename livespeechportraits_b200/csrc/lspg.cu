@@ -6,6 +6,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -16,6 +17,7 @@
 #include <memory>
 #include <string>
 #include <tuple>
+#include <utility>
 #include <vector>
 
 #include "../../include/lspg.h"
@@ -93,9 +95,26 @@ struct PlanLayer {
   ConvParams prm;
   int bn = 64;
   int grid = 1;
+  bool patch = false;     // conv_patch_kernel (halo patch per chunk) instead of conv_umma_kernel (one box per tap)
+  bool split = false;     // split-K: conv kernel writes fp32 partials, splitk_reduce_kernel finishes
+  ReduceParams red;
+  int red_blocks = 0;
+};
+
+struct IoKey {
+  const float* fm; int64_t fm_bstride; const float* cand; int64_t cand_bstride; float* out;
+  bool operator==(const IoKey& o) const {
+    return fm == o.fm && fm_bstride == o.fm_bstride && cand == o.cand && cand_bstride == o.cand_bstride && out == o.out;
+  }
+};
+
+struct GraphEntry {
+  IoKey io;
+  cudaGraphExec_t exec = nullptr;
 };
 
 struct Plan {
+  std::vector<GraphEntry> graphs;      // instantiated CUDA graphs of this plan, keyed by the I/O pointers
   int batch = 0, height = 0, width = 0, mode = 0;
   void* workspace = nullptr;
   std::vector<size_t> tensor_off;            // byte offset of limb 0 of each activation tensor
@@ -118,6 +137,8 @@ struct lspg_ctx {
   EncodeTiledFn encode = nullptr;
   std::map<std::tuple<int, int, int, int, void*>, std::unique_ptr<Plan>> plans;
   Plan* last_plan = nullptr;
+  int num_sms_or_default() const { return num_sms > 0 ? num_sms : 148; }
+  cudaStream_t capture_stream = nullptr;
   bool profiling = false;
   std::vector<std::vector<cudaEvent_t>> prof_events;   // one event set per recorded forward
   size_t prof_used = 0;
@@ -403,10 +424,70 @@ size_t tensor_bytes_one_limb(const TensorInfo& t, int B, int H, int W) {
   return static_cast<size_t>(B) * (H >> t.shift) * (W >> t.shift) * t.channels * 2;
 }
 
+int ilog2(int v) {
+  int l = 0;
+  while ((1 << (l + 1)) <= v) ++l;
+  return l;
+}
+
+// Tiling / kernel-variant decisions of one layer for a problem size (shared by planning and workspace sizing).
+struct Geo {
+  int hs, ws;                  // sampling grid
+  int tw, th, nb;              // output tile = tw x th pixels x nb images (= 128 rows)
+  bool patch;                  // conv_patch_kernel (halo patch) vs conv_umma_kernel (one box per tap)
+  int bn, m_tiles, n_tiles, tiles_per_split;
+  int k_items;                 // K-loop length: K blocks (v1) or (source, chunk) items (patch)
+  int n_split, split_len;
+  size_t partial_bytes;
+};
+
+Geo layer_geo(const lspg_ctx* h, const Layer& L, int B, int H, int W) {
+  static const bool no_patch = getenv("LSPG_NO_PATCH") != nullptr;
+  static const bool no_split = getenv("LSPG_NO_SPLITK") != nullptr;
+  Geo g;
+  g.hs = H >> L.grid_shift; g.ws = W >> L.grid_shift;
+  g.tw = g.ws < 16 ? g.ws : 16;
+  g.th = 128 / g.tw;
+  if (g.th > g.hs) g.th = g.hs;
+  g.nb = 128 / (g.tw * g.th);
+  // patch mode needs 8-pixel-wide tiles (one UMMA 8-row group = one image row of the halo patch)
+  g.patch = !no_patch && L.kind != K_S2 && g.ws >= 8 && g.hs >= 16;
+  if (g.patch) { g.tw = 8; g.th = 16; g.nb = 1; }
+  g.m_tiles = (g.ws / g.tw) * (g.hs / g.th) * ((B + g.nb - 1) / g.nb);
+  const int chunks = L.cin[0] / 64 + (L.n_src == 2 ? L.cin[1] / 64 : 0);
+  g.k_items = g.patch ? chunks : chunks * L.n_taps;
+  if (L.kind == K_TAIL) g.bn = 16;
+  else g.bn = (L.cout_pad % 128 == 0 && g.m_tiles * (L.cout_pad / 128) * L.n_phases >= h->num_sms_or_default()) ? 128 : 64;
+  g.n_tiles = L.cout_pad / g.bn;
+  g.tiles_per_split = g.m_tiles * g.n_tiles * L.n_phases;
+  g.n_split = 1; g.split_len = g.k_items; g.partial_bytes = 0;
+  const int sms = h->num_sms_or_default();
+  if (!no_split && L.kind != K_TAIL && g.tiles_per_split * 2 <= sms) {
+    const int min_len = g.patch ? 1 : 4;                       // at least 4 K blocks (v1) / 1 chunk of all taps per split
+    int want = (sms + g.tiles_per_split - 1) / g.tiles_per_split;
+    int max_split = g.k_items / min_len;
+    if (max_split < 1) max_split = 1;
+    if (want > max_split) want = max_split;
+    if (want > 1) {
+      g.split_len = (g.k_items + want - 1) / want;
+      g.n_split = (g.k_items + g.split_len - 1) / g.split_len;
+      if (g.n_split > 1) g.partial_bytes = static_cast<size_t>(g.n_split) * g.tiles_per_split * kTileM * g.bn * sizeof(float);
+      else g.split_len = g.k_items;
+    }
+  }
+  return g;
+}
+
+size_t scratch_bytes(const lspg_ctx* h, int B, int H, int W) {
+  size_t m = 0;
+  for (const auto& L : h->layers) m = std::max(m, layer_geo(h, L, B, H, W).partial_bytes);
+  return align_up(m, 1024);
+}
+
 size_t workspace_bytes(const lspg_ctx* h, int B, int H, int W, int mode) {
   size_t total = 0;
   for (const auto& t : h->tensors) total += align_up(tensor_bytes_one_limb(t, B, H, W), 1024) * nl_of(mode);
-  return total + 1024;
+  return total + scratch_bytes(h, B, H, W) + 1024;
 }
 
 int check_shape(const lspg_ctx* h, int B, int H, int W, int mode) {
@@ -416,12 +497,6 @@ int check_shape(const lspg_ctx* h, int B, int H, int W, int mode) {
     return fail(LSPG_EINVAL, "height/width must be positive multiples of %d (got %dx%d)", m, H, W);
   if (mode != LSPG_MODE_FAST && mode != LSPG_MODE_PARITY) return fail(LSPG_EINVAL, "unknown precision mode %d", mode);
   return LSPG_OK;
-}
-
-int ilog2(int v) {
-  int l = 0;
-  while ((1 << (l + 1)) <= v) ++l;
-  return l;
 }
 
 // 5-D activation view {C, X, Y, N, limb}; parity/phase views start at (py, px) and step 2 in X and Y.
@@ -468,6 +543,29 @@ int make_weight_map(lspg_ctx* h, CUtensorMap* m, const Layer& L, int bn) {
   return LSPG_OK;
 }
 
+// Patch-mode weight view {kc, Cout, tap, limb*phase}: K of the packed weights is tap-major, so the tap index is a
+// dimension of its own and one TMA box {64, BN, taps_per_stage, 1} fetches the tiles of several taps at once.
+int make_weight_map_taps(lspg_ctx* h, CUtensorMap* m, const Layer& L, int bn, int tps) {
+  const int kt = L.k_total / L.n_taps;       // K elements per tap
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(kt), static_cast<cuuint64_t>(L.cout_pad), static_cast<cuuint64_t>(L.n_taps),
+                        static_cast<cuuint64_t>(2 * L.n_phases)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(L.k_total) * 2, static_cast<cuuint64_t>(kt) * 2,
+                           static_cast<cuuint64_t>(L.k_total) * L.cout_pad * 2};
+  cuuint32_t box[4] = {64u, static_cast<cuuint32_t>(bn), static_cast<cuuint32_t>(tps), 1u};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = h->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, L.d_w, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(LSPG_ECUDA, "cuTensorMapEncodeTiled(weights by tap, K=%d) failed: %d", L.k_total, static_cast<int>(r));
+  return LSPG_OK;
+}
+
+int patch_tps(int bn, int NL, bool tail) {   // must mirror PatchCfg::kTPS
+  if (tail) return 9;
+  if (bn >= 128) return NL == 1 ? 2 : 1;
+  return NL == 1 ? 3 : 2;
+}
+
 uint32_t make_idesc(int bn) {
   // cute::UMMA::InstrDescriptor bit layout: c_format[4,6)=1 (F32), a_format[7,10)=1 (BF16), b_format[10,13)=1,
   // a/b major [15],[16] = 0 (K-major), n_dim[17,23) = N>>3, m_dim[24,29) = M>>4
@@ -498,21 +596,50 @@ int build_plan(lspg_ctx* h, Plan* P, int B, int H, int W, int mode, void* worksp
     off += one * NL;
   }
   uint8_t* ws = static_cast<uint8_t*>(workspace);
+  uint8_t* ws_scratch = ws + align_up(off, 1024);
   for (const Layer& L : h->layers) {
     PlanLayer pl;
     ConvParams& p = pl.prm;
     memset(&p, 0, sizeof(p));
-    const int Hs = H >> L.grid_shift, Ws = W >> L.grid_shift;     // sampling grid
-    int tw = Ws < 16 ? Ws : 16;
-    int th = 128 / tw;
-    if (th > Hs) th = Hs;
-    const int nb = 128 / (tw * th);
-    pl.bn = choose_bn(L);
+    const Geo g = layer_geo(h, L, B, H, W);
+    const int Hs = g.hs, Ws = g.ws;
+    const int tw = g.tw, th = g.th, nb = g.nb;
+    static const bool no_base_offset = getenv("LSPG_DESC_BASE_OFFSET") == nullptr;
+    // Measured on B200 (gpurun bringup2): the UMMA swizzle phase follows the absolute smem address; setting the
+    // descriptor's base-offset field for a 128-byte-shifted start corrupts the result.  Kept as a debug switch.
+    pl.patch = g.patch;
+    int abox_w = tw, abox_h = th, abox_n = nb;
+    if (pl.patch) {
+      int pw = 0, ph = 0;
+      for (int z = 0; z < L.n_phases; ++z) {
+        int dx0 = 127, dx1 = -127, dy0 = 127, dy1 = -127;
+        for (int t = 0; t < L.n_taps; ++t) {
+          dx0 = std::min<int>(dx0, L.tap_dx[z][t]); dx1 = std::max<int>(dx1, L.tap_dx[z][t]);
+          dy0 = std::min<int>(dy0, L.tap_dy[z][t]); dy1 = std::max<int>(dy1, L.tap_dy[z][t]);
+        }
+        p.patch_dx0[z] = static_cast<int8_t>(dx0); p.patch_dy0[z] = static_cast<int8_t>(dy0);
+        pw = std::max(pw, tw + dx1 - dx0); ph = std::max(ph, th + dy1 - dy0);
+      }
+      p.patch_w = pw; p.patch_h = ph;
+      for (int z = 0; z < L.n_phases; ++z)
+        for (int t = 0; t < L.n_taps; ++t)
+          p.tap_row[z][t] = static_cast<int16_t>((L.tap_dy[z][t] - p.patch_dy0[z]) * pw + (L.tap_dx[z][t] - p.patch_dx0[z]));
+      p.desc_base_offset = no_base_offset ? 0 : 1;
+      static const bool tap_rotate = getenv("LSPG_TAP_ROTATE") != nullptr;
+      p.tap_rotate = tap_rotate ? 1 : 0;
+      if (pw * ph * 128 > kPatchSlot) return fail(LSPG_EINVAL, "patch %dx%d does not fit its smem slot", pw, ph);
+      abox_w = pw; abox_h = ph; abox_n = 1;
+    }
+    pl.bn = g.bn;
     p.tw_log2 = ilog2(tw); p.th_log2 = ilog2(th);
     p.tiles_x = Ws / tw; p.tiles_y = Hs / th; p.tiles_n = (B + nb - 1) / nb;
     p.n_tiles = L.cout_pad / pl.bn;
     p.n_phases = L.n_phases;
-    p.total_tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles * p.n_phases;
+    p.tiles_per_split = g.tiles_per_split;
+    p.n_split = g.n_split; p.split_len = g.split_len;
+    p.total_tiles = g.tiles_per_split * g.n_split;
+    p.partial = reinterpret_cast<float*>(ws_scratch);
+    pl.split = g.n_split > 1;
     p.n_taps = L.n_taps; p.n_src = L.n_src;
     p.chunks[0] = L.cin[0] / 64; p.chunks[1] = L.n_src == 2 ? L.cin[1] / 64 : 0;
     p.relu = L.relu; p.has_res = L.res >= 0 ? 1 : 0;
@@ -533,13 +660,17 @@ int build_plan(lspg_ctx* h, Plan* P, int B, int H, int W, int mode, void* worksp
         for (int q = 0; q < 4; ++q)
           if ((rc = make_act_map(h, &p.a[q], tb, ls, NL, t.channels, B, Ht, Wt, true, q >> 1, q & 1, tw, th, nb))) return rc;
       } else {
-        if ((rc = make_act_map(h, &p.a[s], tb, ls, NL, t.channels, B, Ht, Wt, false, 0, 0, tw, th, nb))) return rc;
+        if ((rc = make_act_map(h, &p.a[s], tb, ls, NL, t.channels, B, Ht, Wt, false, 0, 0, abox_w, abox_h, abox_n))) return rc;
       }
     }
     // unused slots still need valid descriptors for prefetch.tensormap
     const int used = (L.kind == K_S2) ? 4 : L.n_src;
     for (int q = used; q < 4; ++q) p.a[q] = p.a[0];
-    if ((rc = make_weight_map(h, &p.w, L, pl.bn))) return rc;
+    if (pl.patch) {
+      if ((rc = make_weight_map_taps(h, &p.w, L, pl.bn, patch_tps(pl.bn, NL, L.kind == K_TAIL)))) return rc;
+    } else {
+      if ((rc = make_weight_map(h, &p.w, L, pl.bn))) return rc;
+    }
     // ---- output / residual views
     if (L.kind != K_TAIL) {
       const TensorInfo& t = h->tensors[L.out];
@@ -555,20 +686,48 @@ int build_plan(lspg_ctx* h, Plan* P, int B, int H, int W, int mode, void* worksp
       }
       if (L.res >= 0) {
         const TensorInfo& r = h->tensors[L.res];
-        if ((rc = make_act_map(h, &p.res, ws + P->tensor_off[L.res], P->tensor_limb_stride[L.res], NL, r.channels, B,
-                               H >> r.shift, W >> r.shift, false, 0, 0, tw, th, nb)))
-          return rc;
-      } else {
-        p.res = p.out[0];
+        p.res_ptr = reinterpret_cast<const __nv_bfloat16*>(ws + P->tensor_off[L.res]);
+        p.res_limb_stride = static_cast<long long>(P->tensor_limb_stride[L.res] / 2);
+        p.res_channels = r.channels;
       }
     } else {
       for (int q = 0; q < 4; ++q) p.out[q] = p.a[0];
-      p.res = p.a[0];
     }
     pl.grid = p.total_tiles < h->num_sms ? p.total_tiles : h->num_sms;
+    if (pl.split) {
+      ReduceParams& r = pl.red;
+      memset(&r, 0, sizeof(r));
+      r.partial = p.partial; r.scale = L.d_scale; r.shift = L.d_shift;
+      r.out = reinterpret_cast<__nv_bfloat16*>(ws + P->tensor_off[L.out]);
+      r.out_limb_stride = static_cast<long long>(P->tensor_limb_stride[L.out] / 2);
+      if (L.res >= 0) {
+        r.res = reinterpret_cast<const __nv_bfloat16*>(ws + P->tensor_off[L.res]);
+        r.res_limb_stride = static_cast<long long>(P->tensor_limb_stride[L.res] / 2);
+      }
+      r.n_split = g.n_split; r.tiles_per_split = g.tiles_per_split; r.m_tiles = g.m_tiles; r.n_tiles = g.n_tiles;
+      r.n_phases = L.n_phases; r.tiles_x = p.tiles_x; r.tiles_y = p.tiles_y; r.tw_log2 = p.tw_log2; r.th_log2 = p.th_log2;
+      r.bn = g.bn; r.batch = B; r.hs = Hs; r.ws = Ws; r.up = (L.kind == K_UP) ? 1 : 0; r.channels = L.cout_pad;
+      r.relu = L.relu; r.has_res = L.res >= 0 ? 1 : 0; r.nl = NL;
+      const long long work = static_cast<long long>(g.tiles_per_split) * kTileM * (g.bn / 8);
+      pl.red_blocks = static_cast<int>(std::min<long long>((work + 127) / 128, 8LL * h->num_sms));
+    }
     P->layers.push_back(pl);
   }
   return LSPG_OK;
+}
+
+// Every kernel of the forward is launched with programmatic stream serialization (PDL): the next kernel's CTAs may
+// be scheduled while this one drains; each kernel calls griddepcontrol.wait before it touches dependent memory.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  static const bool no_pdl = getenv("LSPG_NO_PDL") != nullptr;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = no_pdl ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
 template <int BN, int NL, bool TAIL>
@@ -580,15 +739,81 @@ int launch_conv(const ConvParams& p, int grid, cudaStream_t st) {
                                   Cfg::kSmemBytes));
     configured = true;
   }
-  conv_umma_kernel<BN, NL, TAIL><<<grid, kThreads, Cfg::kSmemBytes, st>>>(p);
-  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(launch_pdl(conv_umma_kernel<BN, NL, TAIL>, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, st, p));
+  return LSPG_OK;
+}
+
+template <int BN, int NL, bool TAIL>
+int launch_patch(const ConvParams& p, int grid, cudaStream_t st) {
+  using Cfg = PatchCfg<BN, NL, TAIL>;
+  static bool configured = false;
+  if (!configured) {
+    CUDA_TRY(cudaFuncSetAttribute(conv_patch_kernel<BN, NL, TAIL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  Cfg::kSmemBytes));
+    configured = true;
+  }
+  CUDA_TRY(launch_pdl(conv_patch_kernel<BN, NL, TAIL>, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, st, p));
   return LSPG_OK;
 }
 
 int launch_layer(const PlanLayer& pl, int kind, int NL, cudaStream_t st) {
+  if (pl.patch) {
+    if (kind == K_TAIL) return NL == 1 ? launch_patch<16, 1, true>(pl.prm, pl.grid, st) : launch_patch<16, 2, true>(pl.prm, pl.grid, st);
+    if (pl.bn == 128) return NL == 1 ? launch_patch<128, 1, false>(pl.prm, pl.grid, st) : launch_patch<128, 2, false>(pl.prm, pl.grid, st);
+    return NL == 1 ? launch_patch<64, 1, false>(pl.prm, pl.grid, st) : launch_patch<64, 2, false>(pl.prm, pl.grid, st);
+  }
   if (kind == K_TAIL) return NL == 1 ? launch_conv<16, 1, true>(pl.prm, pl.grid, st) : launch_conv<16, 2, true>(pl.prm, pl.grid, st);
   if (pl.bn == 128) return NL == 1 ? launch_conv<128, 1, false>(pl.prm, pl.grid, st) : launch_conv<128, 2, false>(pl.prm, pl.grid, st);
   return NL == 1 ? launch_conv<64, 1, false>(pl.prm, pl.grid, st) : launch_conv<64, 2, false>(pl.prm, pl.grid, st);
+}
+
+// Enqueue every kernel of one forward on `st` (plain stream launches; also the body of the graph capture).
+int enqueue_forward(lspg_ctx* h, Plan* P, const IoKey& io, cudaStream_t st, bool debug_sync, bool profile) {
+  const int NL = nl_of(P->mode);
+  const int batch = P->batch, height = P->height, width = P->width;
+  int rc;
+  std::vector<cudaEvent_t>* evs = nullptr;
+  if (profile && h->prof_used < 256) {
+    if (h->prof_used == h->prof_events.size()) {
+      std::vector<cudaEvent_t> set(h->layers.size() + 2);
+      for (auto& e : set) CUDA_TRY(cudaEventCreate(&e));
+      h->prof_events.push_back(set);
+    }
+    evs = &h->prof_events[h->prof_used++];
+    CUDA_TRY(cudaEventRecord((*evs)[0], st));
+  }
+  // 1. input packer (cat + NCHW->NHWC + bf16 + space-to-depth)
+  {
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(static_cast<uint8_t*>(P->workspace) + P->tensor_off[0]);
+    const long long limb_stride = static_cast<long long>(P->tensor_limb_stride[0] / 2);
+    const long long total = static_cast<long long>(batch) * (height / 2) * (width / 2);
+    int blocks = static_cast<int>((total + 127) / 128);
+    if (blocks > h->num_sms * 16) blocks = h->num_sms * 16;
+    const long long fs = io.fm_bstride, cs = io.cand_bstride;
+    if (NL == 1)
+      CUDA_TRY(launch_pdl(pack_input_s2d_kernel<1>, dim3(blocks), dim3(128), 0, st, io.fm, fs, io.cand, cs, h->in_nc, dst, limb_stride, batch, height, width));
+    else
+      CUDA_TRY(launch_pdl(pack_input_s2d_kernel<2>, dim3(blocks), dim3(128), 0, st, io.fm, fs, io.cand, cs, h->in_nc, dst, limb_stride, batch, height, width));
+    if (debug_sync) CUDA_TRY(cudaStreamSynchronize(st));
+    if (evs) CUDA_TRY(cudaEventRecord((*evs)[1], st));
+  }
+  // 2. conv stack
+  for (size_t i = 0; i < h->layers.size(); ++i) {
+    PlanLayer& pl = P->layers[i];
+    if (h->layers[i].kind == K_TAIL) pl.prm.out_f32 = io.out;
+    if ((rc = launch_layer(pl, h->layers[i].kind, NL, st))) return rc;
+    if (pl.split) {
+      CUDA_TRY(launch_pdl(splitk_reduce_kernel, dim3(pl.red_blocks), dim3(128), 0, st, pl.red));
+    }
+    if (evs) CUDA_TRY(cudaEventRecord((*evs)[i + 2], st));
+    if (debug_sync) {
+      cudaError_t e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess)
+        return fail(LSPG_ECUDA, "layer %zu (kind %d, %s, bn %d, grid %d, tiles %d) failed: %s", i, h->layers[i].kind,
+                    h->layers[i].conv_key.c_str(), pl.bn, pl.grid, pl.prm.total_tiles, cudaGetErrorString(e));
+    }
+  }
+  return LSPG_OK;
 }
 
 }  // namespace
@@ -646,6 +871,9 @@ int lspg_destroy(lspg_handle h) {
     }
     for (auto& set : h->prof_events)
       for (auto& e : set) cudaEventDestroy(e);
+    for (auto& kv : h->plans)
+      for (auto& ge : kv.second->graphs) cudaGraphExecDestroy(ge.exec);
+    if (h->capture_stream) cudaStreamDestroy(h->capture_stream);
   }
   delete h;
   return LSPG_OK;
@@ -721,51 +949,47 @@ int lspg_forward(lspg_handle h, const float* feature_map, int64_t fm_bstride, co
   if (it == h->plans.end()) {
     std::unique_ptr<Plan> P(new Plan);
     if ((rc = build_plan(h, P.get(), batch, height, width, mode, workspace))) return rc;
-    if (h->plans.size() > 16) h->plans.clear();
+    if (h->plans.size() > 16) {
+      for (auto& kv : h->plans)
+        for (auto& ge : kv.second->graphs) cudaGraphExecDestroy(ge.exec);
+      h->plans.clear();
+      h->last_plan = nullptr;
+    }
     it = h->plans.emplace(key, std::move(P)).first;
   }
   Plan* P = it->second.get();
   h->last_plan = P;
-  const int NL = nl_of(mode);
-  const bool debug_sync = getenv("LSPG_DEBUG_SYNC") != nullptr;   // per-layer sync + error attribution (bring-up)
-  std::vector<cudaEvent_t>* evs = nullptr;
-  if (h->profiling && h->prof_used < 256) {
-    if (h->prof_used == h->prof_events.size()) {
-      std::vector<cudaEvent_t> set(h->layers.size() + 2);
-      for (auto& e : set) CUDA_TRY(cudaEventCreate(&e));
-      h->prof_events.push_back(set);
+  IoKey io{feature_map, fm_bstride, cand, cand_bstride, out};
+  static const bool no_graph = getenv("LSPG_NO_GRAPH") != nullptr;
+  static const bool debug_sync = getenv("LSPG_DEBUG_SYNC") != nullptr;   // per-layer sync + error attribution (bring-up)
+  if (no_graph || debug_sync || h->profiling) return enqueue_forward(h, P, io, st, debug_sync, h->profiling);
+
+  // CUDA-graph replay: the ~80-120 launches of one forward are captured once per (plan, I/O pointers) on a private
+  // stream (the caller's stream may be the legacy default stream, which cannot be captured) and replayed with a
+  // single cudaGraphLaunch on the caller's stream.
+  for (auto& ge : P->graphs)
+    if (ge.io == io) {
+      CUDA_TRY(cudaGraphLaunch(ge.exec, st));
+      return LSPG_OK;
     }
-    evs = &h->prof_events[h->prof_used++];
-    CUDA_TRY(cudaEventRecord((*evs)[0], st));
+  if (!h->capture_stream) CUDA_TRY(cudaStreamCreateWithFlags(&h->capture_stream, cudaStreamNonBlocking));
+  cudaGraph_t graph = nullptr;
+  CUDA_TRY(cudaStreamBeginCapture(h->capture_stream, cudaStreamCaptureModeThreadLocal));
+  rc = enqueue_forward(h, P, io, h->capture_stream, false, false);
+  cudaError_t ce = cudaStreamEndCapture(h->capture_stream, &graph);
+  if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+  if (ce != cudaSuccess) return fail(LSPG_ECUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(ce));
+  GraphEntry ge;
+  ge.io = io;
+  ce = cudaGraphInstantiate(&ge.exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ce != cudaSuccess) return fail(LSPG_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
+  if (P->graphs.size() >= 16) {                      // bounded cache: drop the oldest instantiation
+    cudaGraphExecDestroy(P->graphs.front().exec);
+    P->graphs.erase(P->graphs.begin());
   }
-  // 1. input packer (cat + NCHW->NHWC + bf16 + space-to-depth)
-  {
-    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(static_cast<uint8_t*>(workspace) + P->tensor_off[0]);
-    const long long limb_stride = static_cast<long long>(P->tensor_limb_stride[0] / 2);
-    const long long total = static_cast<long long>(batch) * (height / 2) * (width / 2);
-    int blocks = static_cast<int>((total + 127) / 128);
-    if (blocks > h->num_sms * 16) blocks = h->num_sms * 16;
-    if (NL == 1)
-      pack_input_s2d_kernel<1><<<blocks, 128, 0, st>>>(feature_map, fm_bstride, cand, cand_bstride, h->in_nc, dst, limb_stride, batch, height, width);
-    else
-      pack_input_s2d_kernel<2><<<blocks, 128, 0, st>>>(feature_map, fm_bstride, cand, cand_bstride, h->in_nc, dst, limb_stride, batch, height, width);
-    CUDA_TRY(cudaGetLastError());
-    if (debug_sync) CUDA_TRY(cudaStreamSynchronize(st));
-    if (evs) CUDA_TRY(cudaEventRecord((*evs)[1], st));
-  }
-  // 2. conv stack
-  for (size_t i = 0; i < h->layers.size(); ++i) {
-    PlanLayer& pl = P->layers[i];
-    if (h->layers[i].kind == K_TAIL) pl.prm.out_f32 = out;
-    if ((rc = launch_layer(pl, h->layers[i].kind, NL, st))) return rc;
-    if (evs) CUDA_TRY(cudaEventRecord((*evs)[i + 2], st));
-    if (debug_sync) {
-      cudaError_t e = cudaStreamSynchronize(st);
-      if (e != cudaSuccess)
-        return fail(LSPG_ECUDA, "layer %zu (kind %d, %s, bn %d, grid %d, tiles %d) failed: %s", i, h->layers[i].kind,
-                    h->layers[i].conv_key.c_str(), pl.bn, pl.grid, pl.prm.total_tiles, cudaGetErrorString(e));
-    }
-  }
+  P->graphs.push_back(ge);
+  CUDA_TRY(cudaGraphLaunch(ge.exec, st));
   return LSPG_OK;
 }
 
@@ -844,7 +1068,10 @@ int lspg_debug_read_tensor(lspg_handle h, int id, int limb, uint16_t* dst, int64
 
 int lspg_launches_per_forward(lspg_handle h, int* out) {
   if (!h || !out) return fail(LSPG_EINVAL, "null argument");
-  *out = 1 + static_cast<int>(h->layers.size());
+  int n = 1 + static_cast<int>(h->layers.size());
+  if (h->last_plan)
+    for (const auto& pl : h->last_plan->layers) n += pl.split ? 1 : 0;   // + split-K finishers of the last plan
+  *out = n;
   return LSPG_OK;
 }
 

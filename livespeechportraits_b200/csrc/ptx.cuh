@@ -18,6 +18,26 @@ __device__ __forceinline__ uint32_t lane_id() {
   return l;
 }
 
+// One lane of a converged warp (elect.sync): unlike `lane == 0`, the compiler knows the guarded region runs in a
+// single thread and emits uniform-datapath instructions (UTCHMMA, UTMALDG, UTCBAR) straight-line instead of
+// wrapping each one in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop (~50 cycles per instruction, measured).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, %1;\n\t"
+      "selp.b32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred)
+      : "r"(0xFFFFFFFFu));
+  return pred != 0;
+}
+
+// ------------------------------------------------------------------ programmatic dependent launch
+// wait: block until the grids this launch depends on have completed and their writes are visible.
+// launch_dependents: allow the next kernel in the stream to start launching (its prologue overlaps our tail).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -51,7 +71,11 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
   return t;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
+  // fast path: a few thousand probes without touching the (slow) global timer
+#pragma unroll 1
+  for (int i = 0; i < 2048; ++i) {
+    if (mbar_try_wait(bar, parity)) return;
+  }
   const uint64_t t0 = globaltimer_ns();
   for (;;) {
 #pragma unroll 1
@@ -70,6 +94,12 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* m, uint64_t* bar,
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_5d(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2,

@@ -239,7 +239,9 @@ class Feature2Face_G(nn.Module):
 
     def profile_read(self) -> Tuple[List[float], int]:
         """(average ms per launch [input packer, conv 0, conv 1, ...], forwards averaged); resets the record."""
-        n = self.launches_per_forward()
+        nl = C.c_int()
+        _lib.check(self._lib.lspg_num_layers(self._info_handle(), C.byref(nl)))
+        n = nl.value + 1                         # input packer + one slot per conv layer (incl. its split-K finisher)
         buf = (C.c_float * n)()
         cnt = C.c_int()
         _lib.check(self._lib.lspg_profile_read(self._handle, buf, n, C.byref(cnt)))

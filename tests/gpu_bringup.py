@@ -144,6 +144,18 @@ def stage_time(variant, recipe, mode, H, B):
     fl = net.flops_per_frame(H, H) * B
     print(f"{variant} {mode} {H} B{B}: {ms:.3f} ms/forward, {B / ms * 1e3:.1f} fps, {fl / ms / 1e9:.1f} TFLOP/s algorithmic",
           flush=True)
+    if os.environ.get("LSPG_PER_LAYER"):
+        net.profile_enable(True)
+        for _ in range(n):
+            net(x)
+        torch.cuda.synchronize()
+        t, cnt = net.profile_read()
+        net.profile_enable(False)
+        rows = net.layer_table(H, H)
+        print(f"  pack_input {t[0] * 1e3:8.1f} us")
+        for i, (r, v) in enumerate(zip(rows, t[1:])):
+            print(f"  L{i:02d} k{r['kind']} {r['cin']:4d}->{r['cout']:3d} @{r['out_h']:3d} {v * 1e3:8.1f} us  "
+                  f"{r['flops'] * B / (v * 1e-3) / 1e12:7.1f} TF/s alg")
     return 0
 
 
