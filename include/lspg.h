@@ -109,6 +109,9 @@ int lspg_num_tensors(lspg_handle h, int* out);
 int lspg_tensor_shape(lspg_handle h, int id, int height, int width, int* c, int* th, int* tw);
 /* Copy activation tensor `id` (bf16 NHWC, limb 0 or 1) of the most recent forward to host memory. */
 int lspg_debug_read_tensor(lspg_handle h, int id, int limb, uint16_t* dst, int64_t count);
+/* Debug: with LSPG_TRACE_LAYER=<i> in the environment the conv kernel of layer i stamps clock64() at its pipeline
+ * milestones (conv_umma.cuh: kTraceSlots values per CTA, 256 CTAs); this copies them out. */
+int lspg_debug_read_trace(lspg_handle h, uint64_t* dst, int64_t count);
 /* Kernels one lspg_forward call launches (for bench.py's gpu_launches accounting). */
 int lspg_launches_per_forward(lspg_handle h, int* out);
 /* Per-launch timing: when enabled, every lspg_forward records a CUDA event on `stream` before its first

@@ -14,7 +14,7 @@ SYMBOLS = [
     "lspg_create", "lspg_load_weights", "lspg_workspace_bytes", "lspg_forward", "lspg_destroy", "lspg_last_error",
     "lspg_num_layers", "lspg_layer_info_get", "lspg_layer_packed", "lspg_layer_affine", "lspg_num_tensors",
     "lspg_tensor_shape", "lspg_debug_read_tensor", "lspg_launches_per_forward", "lspg_flops_per_frame",
-    "lspg_profile_enable", "lspg_profile_read",
+    "lspg_profile_enable", "lspg_profile_read", "lspg_debug_read_trace",
 ]
 
 
@@ -78,6 +78,7 @@ def load(build_if_missing: bool = True) -> C.CDLL:
                                       C.POINTER(C.c_int)]
     lib.lspg_debug_read_tensor.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64]
     lib.lspg_launches_per_forward.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+    lib.lspg_debug_read_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     lib.lspg_profile_enable.argtypes = [C.c_void_p, C.c_int]
     lib.lspg_profile_read.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
     lib.lspg_flops_per_frame.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double)]

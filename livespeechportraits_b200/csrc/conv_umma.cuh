@@ -43,10 +43,14 @@ struct alignas(64) ConvParams {
   const float* scale;        // folded BatchNorm (or 1/0), [Cout_pad]
   const float* shift;
   float* out_f32;            // tail only: fp32 NCHW [B, 3, 2*hs, 2*ws]
+  __nv_bfloat16* out_ptr;         // output tensor (NHWC), limb 0; written directly by the epilogue
+  long long out_limb_stride;      // elements between limbs
+  int32_t out_channels, out_up;   // out_up: the sampling grid is the source of a folded x2 upsample (phase tc.z -> (2y+py, 2x+px))
   const __nv_bfloat16* res_ptr;   // residual tensor (NHWC, same grid as the output), limb 0; read directly by the epilogue
   long long res_limb_stride;      // elements between limbs
   int32_t res_channels;
   uint32_t idesc;            // UMMA instruction descriptor (M=128, N=BN, bf16 x bf16 -> f32, K-major)
+  uint32_t idesc2;           // same with N=2*BN (parity patch kernel: stacked [B_hi;B_lo] operand)
   int32_t n_taps, n_src;
   int32_t chunks[2];         // 64-channel chunks per concat source
   int32_t tiles_x, tiles_y, tiles_n;
@@ -70,6 +74,7 @@ struct alignas(64) ConvParams {
   // partial[tile_index][128][BN]; splitk_reduce_kernel sums the splits and applies the epilogue.
   int32_t n_split, split_len, tiles_per_split;
   float* partial;
+  unsigned long long* trace;     // debug: per-CTA clock64 stamps (null in production), see kTraceSlots
   int32_t tap_rotate;            // patch mode: tile (x,y) dependent rotation of the tap order, so that concurrently
                                  // running CTAs do not all request the same weight tile from L2 at the same time
 };
@@ -78,9 +83,9 @@ template <int BN, int NL, bool TAIL>
 struct ConvCfg {
   static constexpr int kBTile = BN * 128;
   static constexpr int kStage = NL * (kATile + kBTile);
-  static constexpr int kNumStg = TAIL ? 0 : (NL == 1 ? 2 : 1);       // residual-in / result-out staging buffers
+  static constexpr int kNumStg = 0;                                  // (no smem staging: the epilogue writes global memory directly)
   static constexpr int kStgBytes = kNumStg * NL * kATile;
-  static constexpr int kAux = 2048;                                  // scale/shift + barriers + tmem ptr
+  static constexpr int kAux = 3072;                                  // 2 x (scale, shift) + barriers + tmem ptr
   static constexpr int kAvail = kSmemBudget - 1024 /*alignment slack*/ - kStgBytes - kAux;
   static constexpr int kStagesRaw = kAvail / kStage;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
@@ -88,12 +93,24 @@ struct ConvCfg {
   static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
   static_assert(kStages >= 2, "pipeline needs at least two stages");
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "invalid UMMA N");
-  static_assert(2 * BN * 4 + 256 <= kAux, "aux region too small");
+  static_assert(4 * BN * 4 + 256 <= kAux, "aux region too small");
 };
+
+// Debug trace layout per CTA: [0] kernel entry, [1] prologue done, then per local tile i (up to kTraceTiles):
+//   base = 4 + 8*i: +0 MMA got TMEM buffer, +1 MMA first B stage landed, +2 MMA last commit issued,
+//                   +3 EPI waiting for accumulator, +4 EPI accumulator ready, +5 EPI tile done,
+//                   +6 PROD first B load of the tile issued, +7 PROD last B load issued
+constexpr int kTraceTiles = 12;
+constexpr int kTraceSlots = 4 + 8 * kTraceTiles;
+__device__ __forceinline__ void trace_stamp(const ConvParams& p, int slot);
 
 struct TileCoord {
   int z, nt, x0, y0, n0, split;
 };
+
+__device__ __forceinline__ void trace_stamp(const ConvParams& p, int slot) {
+  if (p.trace != nullptr && slot < kTraceSlots) p.trace[static_cast<size_t>(blockIdx.x) * kTraceSlots + slot] = clock64();
+}
 
 __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int t) {
   TileCoord c;
@@ -129,8 +146,11 @@ struct StgCfg {
 
 // Epilogue role (warps 2..5, 128 threads): drains the TMEM accumulators of every tile this CTA owns.
 // NSTG = number of residual-in / result-out staging buffers behind `stg_base`.
-template <int BN, int NL, bool TAIL, int NSTG>
-__device__ __forceinline__ void epilogue_warps(const ConvParams& p, uint8_t* stg_base, float* s_scale, float* s_shift,
+// STACK (parity mode of the patch kernel): the accumulator of a tile is 2*BN columns wide - columns [0,BN) hold
+// A_hi*B_hi + A_lo*B_hi, columns [BN,2BN) hold A_hi*B_lo (one N=2BN MMA over the stacked [B_hi;B_lo] tile) - and the
+// epilogue adds the two halves.
+template <int BN, int NL, bool TAIL, int NSTG, bool STACK>
+__device__ __forceinline__ void epilogue_warps(const ConvParams& p, uint8_t* stg_base, float* s_scale0, float* /*unused*/,
                                                uint64_t* tfull_bar, uint64_t* tempty_bar, uint64_t* stg_bar,
                                                uint32_t tmem_base, int warp, int lane) {
   using Cfg = StgCfg<NSTG>;
@@ -145,9 +165,14 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, uint8_t* stg
     uint32_t g = 0;                             // running staging-chunk counter (selects buffer + parity)
 
     constexpr int kChunksPerTile = TAIL ? 1 : BN / kChunk;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+    int lt = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++lt) {
       const TileCoord tc = decode_tile(p, t);
-      // folded BatchNorm parameters of this tile's channel range
+      if (leader) trace_stamp(p, 4 + 8 * lt + 3);
+      // folded BatchNorm parameters of this tile's channel range, double buffered by accumulator index: a warp that
+      // is already on the next tile must not overwrite values a slower warp still reads (no barrier after the math)
+      float* s_scale = s_scale0 + acc * 2 * BN;
+      float* s_shift = s_scale + BN;
       for (int i = etid; i < BN; i += kEpiThreads) {
         s_scale[i] = p.scale[tc.nt * BN + i];
         s_shift[i] = p.shift[tc.nt * BN + i];
@@ -157,12 +182,21 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, uint8_t* stg
 
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
       ptx::tc_fence_after();
-      const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+      if (leader) trace_stamp(p, 4 + 8 * lt + 4);
+      constexpr int kAccCols = STACK ? 2 * BN : BN;
+      const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccCols;
 
       if constexpr (TAIL) {
         // ---- tail: 16 columns = 4 phases x 3 channels (+4 pad); tanh; fp32 NCHW scatter
         uint32_t v[16];
         ptx::tmem_ld_32x16(t_acc, v);
+        if constexpr (STACK) {
+          uint32_t v2[16];
+          ptx::tmem_ld_32x16(t_acc + BN, v2);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
+        }
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
         __syncwarp();
@@ -195,6 +229,13 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, uint8_t* stg
         for (int c32 = 0; c32 < BN / 32; ++c32) {
           uint32_t v[32];
           ptx::tmem_ld_32x32(t_acc + c32 * 32, v);
+          if constexpr (STACK) {
+            uint32_t v2[32];
+            ptx::tmem_ld_32x32(t_acc + BN + c32 * 32, v2);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
+          }
           ptx::tmem_ld_wait();
           if (c32 == BN / 32 - 1) {
             ptx::tc_fence_before();
@@ -206,20 +247,39 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, uint8_t* stg
             *reinterpret_cast<uint4*>(dst + c32 * 32 + e * 4) = make_uint4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
         }
       } else {
-        // ---- regular: scale/shift (+ residual, read straight from global: this thread's own pixel row) + ReLU,
-        //      bf16 (hi, lo) into a swizzled staging tile, TMA store.  kNumStg staging buffers rotate; the only wait
-        //      on a previous store sits right before the smem writes, after the TMEM loads and the math.
+        // ---- regular: scale/shift (+ residual) + ReLU, bf16 (hi, lo), written straight to the NHWC output.
+        // Each thread owns one pixel: it reads its residual row and writes its output row (64 channels = 128
+        // contiguous bytes per chunk and limb) with plain 16-byte global accesses.  No smem staging and no TMA
+        // store: a TMA store queues behind the producer's outstanding TMA loads in the SM's TMA pipe, and waiting
+        // for its smem read cost ~3 us per 64-channel chunk (measured), which made the epilogue - not the tensor
+        // pipe - the per-tile critical path.  Global stores are fire-and-forget.
         const int tw_ = row & ((1 << p.tw_log2) - 1);
         const int th_ = (row >> p.tw_log2) & ((1 << p.th_log2) - 1);
         const int nb_ = row >> (p.tw_log2 + p.th_log2);
         const int pn = tc.n0 + nb_, py_ = tc.y0 + th_, px_ = tc.x0 + tw_;
         const bool pix_ok = pn < p.batch && py_ < p.hs && px_ < p.ws;
+        const int oh = p.out_up ? 2 * p.hs : p.hs, ow = p.out_up ? 2 * p.ws : p.ws;
+        const int oy = p.out_up ? 2 * py_ + (tc.z >> 1) : py_, ox = p.out_up ? 2 * px_ + (tc.z & 1) : px_;
+        __nv_bfloat16* out_row = p.out_ptr + ((static_cast<size_t>(pn) * oh + oy) * ow + ox) * p.out_channels + tc.nt * BN;
         const __nv_bfloat16* res_row = p.res_ptr + ((static_cast<size_t>(pn) * p.hs + py_) * p.ws + px_) * p.res_channels +
                                        tc.nt * BN;
-        for (int chunk = 0; chunk < kChunksPerTile; ++chunk, ++g) {
-          const int j = g % Cfg::kNumStg;
-          uint8_t* buf = stg_base + j * NL * kATile;
-          uint8_t* my_row = buf + row * 128;
+        if (p.has_res) {
+          // pull the residual rows of this CTA's NEXT tile towards L2 while this tile is being finished
+          const int t2 = t + gridDim.x;
+          if (t2 < p.total_tiles) {
+            const TileCoord tc2 = decode_tile(p, t2);
+            const int n2 = tc2.n0 + nb_, y2 = tc2.y0 + th_, x2 = tc2.x0 + tw_;
+            if (n2 < p.batch && y2 < p.hs && x2 < p.ws) {
+              const __nv_bfloat16* r2 = p.res_ptr + ((static_cast<size_t>(n2) * p.hs + y2) * p.ws + x2) * p.res_channels + tc2.nt * BN;
+#pragma unroll
+              for (int l = 0; l < NL; ++l)
+#pragma unroll
+                for (int c = 0; c < kChunksPerTile; ++c)
+                  asm volatile("prefetch.global.L2 [%0];" ::"l"(r2 + l * p.res_limb_stride + c * kChunk));
+            }
+          }
+        }
+        for (int chunk = 0; chunk < kChunksPerTile; ++chunk) {
           uint4 rs[NL][8];                                   // residual: 64 channels x NL limbs of this pixel
           if (p.has_res) {
 #pragma unroll
@@ -232,6 +292,16 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, uint8_t* stg
           uint32_t vv[2][32];
           ptx::tmem_ld_32x32(t_acc + chunk * kChunk, vv[0]);
           ptx::tmem_ld_32x32(t_acc + chunk * kChunk + 32, vv[1]);
+          if constexpr (STACK) {
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+              uint32_t v2[32];
+              ptx::tmem_ld_32x32(t_acc + BN + chunk * kChunk + hf * 32, v2);
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) vv[hf][i] = __float_as_uint(__uint_as_float(vv[hf][i]) + __uint_as_float(v2[i]));
+            }
+          }
           ptx::tmem_ld_wait();
           if (chunk == kChunksPerTile - 1) {
             // accumulator fully drained into registers: hand the TMEM buffer back to the MMA warp
@@ -239,12 +309,8 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, uint8_t* stg
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
           }
-          // staging buffer j is free once the store issued kNumStg chunks ago has finished reading it
-          if (leader) ptx::tma_store_wait_read<Cfg::kNumStg - 1>();
-          ptx::named_bar_sync(3, kEpiThreads);
 #pragma unroll
           for (int piece = 0; piece < 8; ++piece) {          // 16-byte pieces: 8 channels each
-            const int phys = (piece ^ (row & 7)) << 4;       // 128B swizzle
             float y[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
@@ -271,30 +337,23 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, uint8_t* stg
             o.y = pack_bf16x2(y[2], y[3]);
             o.z = pack_bf16x2(y[4], y[5]);
             o.w = pack_bf16x2(y[6], y[7]);
-            *reinterpret_cast<uint4*>(my_row + phys) = o;
+            if (pix_ok) *reinterpret_cast<uint4*>(out_row + chunk * kChunk + piece * 8) = o;
             if (NL == 2) {
               const uint32_t oo[4] = {o.x, o.y, o.z, o.w};
               uint32_t lo[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e)
                 lo[e] = pack_bf16x2(y[2 * e] - bf16_lo(oo[e]), y[2 * e + 1] - bf16_hi(oo[e]));
-              *reinterpret_cast<uint4*>(my_row + kATile + phys) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+              if (pix_ok)
+                *reinterpret_cast<uint4*>(out_row + p.out_limb_stride + chunk * kChunk + piece * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             }
-          }
-          ptx::fence_proxy_async_smem();
-          ptx::named_bar_sync(2, kEpiThreads);
-          if (leader) {
-#pragma unroll
-            for (int l = 0; l < NL; ++l)
-              ptx::tma_store_5d(&p.out[tc.z], buf + l * kATile, tc.nt * BN + chunk * kChunk, tc.x0, tc.y0, tc.n0, l);
-            ptx::tma_store_commit();
           }
         }
        }
       }
+      if (leader) trace_stamp(p, 4 + 8 * lt + 5);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (!TAIL && leader) ptx::tma_store_wait_all<0>();   // global writes complete before the CTA retires
 }
 
 template <int BN, int NL, bool TAIL>
@@ -306,7 +365,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   uint8_t* aux = stg_base + Cfg::kStgBytes;
   float* s_scale = reinterpret_cast<float*>(aux);
   float* s_shift = s_scale + BN;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(aux + 2 * BN * 4);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(aux + 4 * BN * 4);
   uint64_t* full_bar = bars;                       // [kStages]
   uint64_t* empty_bar = bars + Cfg::kStages;       // [kStages]
   uint64_t* tfull_bar = bars + 2 * Cfg::kStages;   // [2]
@@ -422,7 +481,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
-    epilogue_warps<BN, NL, TAIL, Cfg::kNumStg>(p, stg_base, s_scale, s_shift, tfull_bar, tempty_bar, stg_bar, tmem_base, warp, lane);
+    epilogue_warps<BN, NL, TAIL, Cfg::kNumStg, false>(p, stg_base, s_scale, s_shift, tfull_bar, tempty_bar, stg_bar, tmem_base, warp, lane);
   }
 
   ptx::tc_fence_before();
@@ -445,8 +504,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
 // TMA wrote are read back consistently at any 128-byte-aligned start (descriptor base offset = (start>>7)&7).
 // A and B move through separate mbarrier rings: an A patch is consumed by n_taps B tiles.
 // ====================================================================================================
-constexpr int kPatchSlot = 23 * 1024 + 512;     // >= 10*18*128 bytes, multiple of 512; slots are 1024-aligned via kPatchStride
-constexpr int kPatchStride = 24 * 1024;
+constexpr int kPatchSlot = 23 * 1024;           // >= 10*18*128 = 23040 bytes
+constexpr int kPatchStride = 23 * 1024;         // distance between patch buffers (1024-byte aligned)
 
 template <int BN, int NL, bool TAIL>
 struct PatchCfg {
@@ -456,17 +515,23 @@ struct PatchCfg {
   static constexpr int kTPS = TAIL ? 9 : (BN >= 128 ? (NL == 1 ? 2 : 1) : (NL == 1 ? 3 : 2));
   static constexpr int kAStage = NL * kPatchStride;
   static constexpr int kBStage = NL * kTPS * kBTile;
-  static constexpr int kAStages = (NL == 1) ? 3 : 2;
-  static constexpr int kNumStg = TAIL ? 0 : (NL == 1 ? 2 : 1);
+  // In-kernel clock64 traces (tests/gpu_trace.py) showed the MMA warp stalling ~350 cycles per B stage: a stage is
+  // refilled only after the MMAs that read it retire, and the refill (barrier -> TMA issue -> L2 -> smem) takes
+  // ~2.3-2.7k cycles, so the B ring must hold more than that much tensor work.  Two A patches are enough (the next
+  // one is requested a full chunk ahead); everything else goes to B stages.
+  static constexpr int kAStages = 2;
+  static constexpr int kNumStg = 0;
   static constexpr int kStgBytes = kNumStg * NL * kATile;
-  static constexpr int kAux = 2048;
+  static constexpr int kAux = 3072;
   static constexpr int kAvail = kSmemBudget - 1024 - kStgBytes - kAux - kAStages * kAStage;
   static constexpr int kBStagesRaw = kAvail / kBStage;
-  static constexpr int kBStages = kBStagesRaw > 8 ? 8 : kBStagesRaw;
+  static constexpr int kBStages = kBStagesRaw > 12 ? 12 : kBStagesRaw;
   static constexpr int kSmemBytes = 1024 + kAStages * kAStage + kBStages * kBStage + kStgBytes + kAux;
-  static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
+  static constexpr int kAccCols = (NL == 2) ? 2 * BN : BN;                   // parity: stacked [hi*hi+lo*hi | hi*lo] accumulator
+  static constexpr int kTmemCols = (2 * kAccCols < 32) ? 32 : 2 * kAccCols;
+  static_assert(kTmemCols <= 512, "TMEM has 512 columns");
   static_assert(kBStages >= 2, "B ring needs at least two stages");
-  static_assert(2 * BN * 4 + (2 * 8 + 2 * 3 + 8) * 8 <= kAux, "aux region too small");
+  static_assert(4 * BN * 4 + (2 * 12 + 2 * 2 + 8) * 8 <= kAux, "aux region too small");
 };
 
 __device__ __forceinline__ uint64_t umma_desc_sw128_strided(uint32_t smem_addr, uint32_t sbo_bytes, bool base_off) {
@@ -480,7 +545,12 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_strided(uint32_t smem_addr, 
   return d;
 }
 
-template <int BN, int NL, bool TAIL>
+// CL = cluster size (1 or 2).  With CL = 2 the two CTAs of a cluster work on neighbouring M tiles of the same N tile and
+// phase, so they consume identical B stages: each CTA fetches half the rows of every weight tile and multicasts them
+// to both (cp.async.bulk.tensor ... .multicast::cluster), halving the L2->SM weight traffic that clock64 traces showed
+// to be the limiter (~30-36 B/clk/SM of weight tiles, every SM asking L2 for the same lines).  A stage is refilled
+// only after BOTH CTAs' MMAs released it (tcgen05.commit ... .multicast::cluster onto both bempty barriers).
+template <int BN, int NL, bool TAIL, int CL>
 __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_constant__ ConvParams p) {
   using Cfg = PatchCfg<BN, NL, TAIL>;
   extern __shared__ uint8_t smem_raw[];
@@ -491,7 +561,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
   uint8_t* aux = stg_base + Cfg::kStgBytes;
   float* s_scale = reinterpret_cast<float*>(aux);
   float* s_shift = s_scale + BN;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(aux + 2 * BN * 4);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(aux + 4 * BN * 4);
   uint64_t* afull_bar = bars;                               // [kAStages]
   uint64_t* aempty_bar = afull_bar + Cfg::kAStages;         // [kAStages]
   uint64_t* bfull_bar = aempty_bar + Cfg::kAStages;         // [kBStages]
@@ -503,6 +573,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);   // provably warp-uniform
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) trace_stamp(p, 0);
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 4; ++i) ptx::prefetch_tmap(&p.a[i]);
@@ -511,7 +582,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
       for (int i = 0; i < 4; ++i) ptx::prefetch_tmap(&p.out[i]);
     }
     for (int i = 0; i < Cfg::kAStages; ++i) { ptx::mbar_init(&afull_bar[i], 1); ptx::mbar_init(&aempty_bar[i], 1); }
-    for (int i = 0; i < Cfg::kBStages; ++i) { ptx::mbar_init(&bfull_bar[i], 1); ptx::mbar_init(&bempty_bar[i], 1); }
+    for (int i = 0; i < Cfg::kBStages; ++i) { ptx::mbar_init(&bfull_bar[i], 1); ptx::mbar_init(&bempty_bar[i], CL); }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tfull_bar[i], 1);
       ptx::mbar_init(&tempty_bar[i], 4);
@@ -525,9 +596,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (CL > 1) ptx::cluster_sync();     // peers' barriers are initialised before anyone multicasts into them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t crank = (CL > 1) ? ptx::cluster_ctarank() : 0u;
+  constexpr uint16_t kMask = static_cast<uint16_t>((1u << CL) - 1u);
   ptx::pdl_launch_dependents();   // the next kernel may start its prologue; it waits (pdl_wait) before touching our output
+  if (threadIdx.x == 0) trace_stamp(p, 1);
 
   int kb_per_tap = 0;
   for (int s = 0; s < p.n_src; ++s) kb_per_tap += p.chunks[s];   // = (source, chunk) items per tile
@@ -564,26 +639,47 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
     issue_a();
     const int n_groups = (p.n_taps + Cfg::kTPS - 1) / Cfg::kTPS;
     const int a_after_group = (n_groups > 1) ? 1 : 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+    int lt = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++lt) {
       const TileCoord tc = decode_tile(p, t);
       const int ci0 = tc.split * p.split_len;
       const int ci1 = (ci0 + p.split_len < kb_per_tap) ? ci0 + p.split_len : kb_per_tap;
+      if (lane == 0) trace_stamp(p, 4 + 8 * lt + 6);
       for (int ci = ci0; ci < ci1; ++ci) {
         for (int g = 0; g < n_groups; ++g) {
           ptx::mbar_wait(&bempty_bar[ib], phb ^ 1);
           if (ptx::elect_one()) {
             uint8_t* st = b_ring + ib * Cfg::kBStage;
-            ptx::mbar_expect_tx(&bfull_bar[ib], Cfg::kBStage);
+            if constexpr (CL == 1 && NL == 1) {
+              ptx::mbar_expect_tx(&bfull_bar[ib], Cfg::kBStage);
+              // one box = kTPS taps x BN rows x 64 channels (taps beyond n_taps are zero-filled)
+              ptx::tma_load_4d(&p.w, &bfull_bar[ib], st, ci * kChunk, tc.nt * BN, g * Cfg::kTPS, tc.z);
+            } else {
+              // per-tap boxes of BN/CL rows.  Stage layout [tap][limb][BN rows]: B_lo follows B_hi so that one N=2*BN
+              // descriptor covers the stacked pair.  With CL = 2 this CTA fetches rows [crank*BN/CL, +BN/CL) of every
+              // tile and multicasts them to the whole cluster.
+              const int tap0 = g * Cfg::kTPS;
+              const int ntap = (tap0 + Cfg::kTPS < p.n_taps) ? Cfg::kTPS : p.n_taps - tap0;
+              ptx::mbar_expect_tx(&bfull_bar[ib], NL * ntap * Cfg::kBTile);
+              constexpr int kRows = BN / CL;
+              for (int ti = 0; ti < ntap; ++ti)
 #pragma unroll
-            for (int l = 0; l < NL; ++l)   // one box = kTPS taps x BN rows x 64 channels (taps beyond n_taps are zero-filled)
-              ptx::tma_load_4d(&p.w, &bfull_bar[ib], st + l * Cfg::kTPS * Cfg::kBTile, ci * kChunk, tc.nt * BN, g * Cfg::kTPS,
-                               l * p.n_phases + tc.z);
+                for (int l = 0; l < NL; ++l) {
+                  uint8_t* dst = st + (ti * NL + l) * Cfg::kBTile + crank * kRows * 128;
+                  if constexpr (CL == 1)
+                    ptx::tma_load_4d(&p.w, &bfull_bar[ib], dst, ci * kChunk, tc.nt * BN, tap0 + ti, l * p.n_phases + tc.z);
+                  else
+                    ptx::tma_load_4d_mc(&p.w, &bfull_bar[ib], dst, ci * kChunk, tc.nt * BN + crank * kRows, tap0 + ti,
+                                        l * p.n_phases + tc.z, kMask);
+                }
+            }
           }
           __syncwarp();
           if (++ib == Cfg::kBStages) { ib = 0; phb ^= 1; }
           if (g == a_after_group) issue_a();
         }
       }
+      if (lane == 0) trace_stamp(p, 4 + 8 * lt + 7);
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
@@ -595,11 +691,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
     const bool boff = p.desc_base_offset != 0;
     const int n_groups = (p.n_taps + Cfg::kTPS - 1) / Cfg::kTPS;
     bool b_ready = false;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+    int lt = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++lt) {
       const TileCoord tc = decode_tile(p, t);
       ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       ptx::tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * BN;
+      if (lane == 0) trace_stamp(p, 4 + 8 * lt + 0);
+      const uint32_t d_tmem = tmem_base + acc * Cfg::kAccCols;
       const int ci0 = tc.split * p.split_len;
       const int ci1 = (ci0 + p.split_len < kb_per_tap) ? ci0 + p.split_len : kb_per_tap;
       for (int ci = ci0; ci < ci1; ++ci) {
@@ -608,28 +706,31 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
         for (int g = 0; g < n_groups; ++g) {
           if (!b_ready) ptx::mbar_wait(&bfull_bar[ib], phb);
           ptx::tc_fence_after();
+          if (lane == 0 && ci == ci0 && g == 0) trace_stamp(p, 4 + 8 * lt + 1);
           const int tap0 = g * Cfg::kTPS;
           const int tap1 = (tap0 + Cfg::kTPS < p.n_taps) ? tap0 + Cfg::kTPS : p.n_taps;
           if (ptx::elect_one()) {
             const uint32_t b0 = ptx::smem_u32(b_ring + ib * Cfg::kBStage);
             for (int tap = tap0; tap < tap1; ++tap) {
               const uint32_t a_hi_addr = a0 + static_cast<uint32_t>(p.tap_row[tc.z][tap]) * 128u;
-              const uint32_t b_hi_addr = b0 + static_cast<uint32_t>(tap - tap0) * Cfg::kBTile;
+              const uint32_t b_hi_addr = b0 + static_cast<uint32_t>(tap - tap0) * (NL * Cfg::kBTile);
               const uint64_t a_hi = umma_desc_sw128_strided(a_hi_addr, sbo, boff);
               const uint64_t b_hi = ptx::umma_desc_sw128(b_hi_addr);
 #pragma unroll
               for (int k = 0; k < kChunk / 16; ++k) {
                 const uint32_t accum = (ci > ci0 || tap > 0 || k > 0) ? 1u : 0u;
-                ptx::umma_f16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, p.idesc, accum);
-                if (NL == 2) {
+                if constexpr (NL == 1) {
+                  ptx::umma_f16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, p.idesc, accum);
+                } else {
+                  // [hi*hi | hi*lo] in one N=2*BN MMA (B_lo is stored right behind B_hi), then lo*hi into the first half
                   const uint64_t a_lo = umma_desc_sw128_strided(a_hi_addr + kPatchStride, sbo, boff);
-                  const uint64_t b_lo = ptx::umma_desc_sw128(b_hi_addr + Cfg::kTPS * Cfg::kBTile);
-                  ptx::umma_f16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, p.idesc, 1u);
+                  ptx::umma_f16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, p.idesc2, accum);
                   ptx::umma_f16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, p.idesc, 1u);
                 }
               }
             }
-            ptx::umma_commit(&bempty_bar[ib]);
+            if constexpr (CL == 1) ptx::umma_commit(&bempty_bar[ib]);
+            else ptx::umma_commit_mc(&bempty_bar[ib], kMask);     // the stage is shared: release it in every CTA
             if (g == n_groups - 1) {
               ptx::umma_commit(&aempty_bar[ia]);
               if (ci == ci1 - 1) ptx::umma_commit(&tfull_bar[acc]);
@@ -641,14 +742,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
         }
         if (++ia == Cfg::kAStages) { ia = 0; pha ^= 1; }
       }
+      if (lane == 0) trace_stamp(p, 4 + 8 * lt + 2);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
-    epilogue_warps<BN, NL, TAIL, Cfg::kNumStg>(p, stg_base, s_scale, s_shift, tfull_bar, tempty_bar, stg_bar, tmem_base, warp, lane);
+    epilogue_warps<BN, NL, TAIL, Cfg::kNumStg, (NL == 2)>(p, stg_base, s_scale, s_shift, tfull_bar, tempty_bar, stg_bar, tmem_base, warp, lane);
   }
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (CL > 1) ptx::cluster_sync();     // no CTA leaves while a peer may still signal its barriers / write its smem
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);

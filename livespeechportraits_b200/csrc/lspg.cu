@@ -96,6 +96,7 @@ struct PlanLayer {
   int bn = 64;
   int grid = 1;
   bool patch = false;     // conv_patch_kernel (halo patch per chunk) instead of conv_umma_kernel (one box per tap)
+  int cluster = 1;        // CTAs per cluster sharing B stages by TMA multicast (patch mode only)
   bool split = false;     // split-K: conv kernel writes fp32 partials, splitk_reduce_kernel finishes
   ReduceParams red;
   int red_blocks = 0;
@@ -139,6 +140,7 @@ struct lspg_ctx {
   Plan* last_plan = nullptr;
   int num_sms_or_default() const { return num_sms > 0 ? num_sms : 148; }
   cudaStream_t capture_stream = nullptr;
+  unsigned long long* trace_buf = nullptr;   // debug (LSPG_TRACE_LAYER): clock64 stamps of one layer's CTAs
   bool profiling = false;
   std::vector<std::vector<cudaEvent_t>> prof_events;   // one event set per recorded forward
   size_t prof_used = 0;
@@ -545,7 +547,7 @@ int make_weight_map(lspg_ctx* h, CUtensorMap* m, const Layer& L, int bn) {
 
 // Patch-mode weight view {kc, Cout, tap, limb*phase}: K of the packed weights is tap-major, so the tap index is a
 // dimension of its own and one TMA box {64, BN, taps_per_stage, 1} fetches the tiles of several taps at once.
-int make_weight_map_taps(lspg_ctx* h, CUtensorMap* m, const Layer& L, int bn, int tps) {
+int make_weight_map_taps(lspg_ctx* h, CUtensorMap* m, const Layer& L, int bn, int tps) {   // bn = box rows, tps = box taps
   const int kt = L.k_total / L.n_taps;       // K elements per tap
   cuuint64_t dims[4] = {static_cast<cuuint64_t>(kt), static_cast<cuuint64_t>(L.cout_pad), static_cast<cuuint64_t>(L.n_taps),
                         static_cast<cuuint64_t>(2 * L.n_phases)};
@@ -645,6 +647,7 @@ int build_plan(lspg_ctx* h, Plan* P, int B, int H, int W, int mode, void* worksp
     p.relu = L.relu; p.has_res = L.res >= 0 ? 1 : 0;
     p.batch = B; p.hs = Hs; p.ws = Ws;
     p.idesc = make_idesc(pl.bn);
+    p.idesc2 = make_idesc(2 * pl.bn);
     p.scale = L.d_scale; p.shift = L.d_shift; p.out_f32 = nullptr;
     memcpy(p.tap_map, L.tap_map, sizeof(p.tap_map));
     memcpy(p.tap_dx, L.tap_dx, sizeof(p.tap_dx));
@@ -667,7 +670,11 @@ int build_plan(lspg_ctx* h, Plan* P, int B, int H, int W, int mode, void* worksp
     const int used = (L.kind == K_S2) ? 4 : L.n_src;
     for (int q = used; q < 4; ++q) p.a[q] = p.a[0];
     if (pl.patch) {
-      if ((rc = make_weight_map_taps(h, &p.w, L, pl.bn, patch_tps(pl.bn, NL, L.kind == K_TAIL)))) return rc;
+      static const bool no_cluster = getenv("LSPG_NO_CLUSTER") != nullptr;
+      pl.cluster = (!no_cluster && g.n_split == 1 && g.m_tiles % 2 == 0 && g.tiles_per_split >= h->num_sms) ? 2 : 1;
+      if (pl.cluster == 1 && NL == 1) rc = make_weight_map_taps(h, &p.w, L, pl.bn, patch_tps(pl.bn, NL, L.kind == K_TAIL));
+      else rc = make_weight_map_taps(h, &p.w, L, pl.bn / pl.cluster, 1);      // per-tap boxes (row slice per CTA when multicasting)
+      if (rc) return rc;
     } else {
       if ((rc = make_weight_map(h, &p.w, L, pl.bn))) return rc;
     }
@@ -684,6 +691,10 @@ int build_plan(lspg_ctx* h, Plan* P, int B, int H, int W, int mode, void* worksp
         if ((rc = make_act_map(h, &p.out[0], tb, ls, NL, t.channels, B, Ht, Wt, false, 0, 0, tw, th, nb))) return rc;
         for (int q = 1; q < 4; ++q) p.out[q] = p.out[0];
       }
+      p.out_ptr = reinterpret_cast<__nv_bfloat16*>(tb);
+      p.out_limb_stride = static_cast<long long>(ls / 2);
+      p.out_channels = t.channels;
+      p.out_up = (L.kind == K_UP) ? 1 : 0;
       if (L.res >= 0) {
         const TensorInfo& r = h->tensors[L.res];
         p.res_ptr = reinterpret_cast<const __nv_bfloat16*>(ws + P->tensor_off[L.res]);
@@ -694,6 +705,15 @@ int build_plan(lspg_ctx* h, Plan* P, int B, int H, int W, int mode, void* worksp
       for (int q = 0; q < 4; ++q) p.out[q] = p.a[0];
     }
     pl.grid = p.total_tiles < h->num_sms ? p.total_tiles : h->num_sms;
+    if (pl.cluster > 1) pl.grid -= pl.grid % pl.cluster;
+    {
+      const char* tl = getenv("LSPG_TRACE_LAYER");
+      if (tl && atoi(tl) == static_cast<int>(P->layers.size())) {
+        if (!h->trace_buf) CUDA_TRY(cudaMalloc(&h->trace_buf, sizeof(unsigned long long) * 256 * kTraceSlots));
+        CUDA_TRY(cudaMemset(h->trace_buf, 0, sizeof(unsigned long long) * 256 * kTraceSlots));
+        p.trace = h->trace_buf;
+      }
+    }
     if (pl.split) {
       ReduceParams& r = pl.red;
       memset(&r, 0, sizeof(r));
@@ -719,15 +739,32 @@ int build_plan(lspg_ctx* h, Plan* P, int B, int H, int W, int mode, void* worksp
 // Every kernel of the forward is launched with programmatic stream serialization (PDL): the next kernel's CTAs may
 // be scheduled while this one drains; each kernel calls griddepcontrol.wait before it touches dependent memory.
 template <typename... KArgs, typename... Args>
-cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+cudaError_t launch_pdl_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster,
+                               Args&&... args) {
   static const bool no_pdl = getenv("LSPG_NO_PDL") != nullptr;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = no_pdl ? 0 : 1;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (!no_pdl) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = static_cast<unsigned>(cluster);
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  cfg.attrs = attr; cfg.numAttrs = n;
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  return launch_pdl_cluster(kernel, grid, block, smem, st, 1, std::forward<Args>(args)...);
 }
 
 template <int BN, int NL, bool TAIL>
@@ -743,24 +780,30 @@ int launch_conv(const ConvParams& p, int grid, cudaStream_t st) {
   return LSPG_OK;
 }
 
-template <int BN, int NL, bool TAIL>
+template <int BN, int NL, bool TAIL, int CL>
 int launch_patch(const ConvParams& p, int grid, cudaStream_t st) {
   using Cfg = PatchCfg<BN, NL, TAIL>;
   static bool configured = false;
   if (!configured) {
-    CUDA_TRY(cudaFuncSetAttribute(conv_patch_kernel<BN, NL, TAIL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CUDA_TRY(cudaFuncSetAttribute(conv_patch_kernel<BN, NL, TAIL, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   Cfg::kSmemBytes));
     configured = true;
   }
-  CUDA_TRY(launch_pdl(conv_patch_kernel<BN, NL, TAIL>, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, st, p));
+  CUDA_TRY(launch_pdl_cluster(conv_patch_kernel<BN, NL, TAIL, CL>, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, st, CL, p));
   return LSPG_OK;
+}
+
+template <int BN, int NL, bool TAIL>
+int launch_patch_cl(const ConvParams& p, int grid, int cluster, cudaStream_t st) {
+  return cluster == 2 ? launch_patch<BN, NL, TAIL, 2>(p, grid, st) : launch_patch<BN, NL, TAIL, 1>(p, grid, st);
 }
 
 int launch_layer(const PlanLayer& pl, int kind, int NL, cudaStream_t st) {
   if (pl.patch) {
-    if (kind == K_TAIL) return NL == 1 ? launch_patch<16, 1, true>(pl.prm, pl.grid, st) : launch_patch<16, 2, true>(pl.prm, pl.grid, st);
-    if (pl.bn == 128) return NL == 1 ? launch_patch<128, 1, false>(pl.prm, pl.grid, st) : launch_patch<128, 2, false>(pl.prm, pl.grid, st);
-    return NL == 1 ? launch_patch<64, 1, false>(pl.prm, pl.grid, st) : launch_patch<64, 2, false>(pl.prm, pl.grid, st);
+    const int c = pl.cluster;
+    if (kind == K_TAIL) return NL == 1 ? launch_patch_cl<16, 1, true>(pl.prm, pl.grid, c, st) : launch_patch_cl<16, 2, true>(pl.prm, pl.grid, c, st);
+    if (pl.bn == 128) return NL == 1 ? launch_patch_cl<128, 1, false>(pl.prm, pl.grid, c, st) : launch_patch_cl<128, 2, false>(pl.prm, pl.grid, c, st);
+    return NL == 1 ? launch_patch_cl<64, 1, false>(pl.prm, pl.grid, c, st) : launch_patch_cl<64, 2, false>(pl.prm, pl.grid, c, st);
   }
   if (kind == K_TAIL) return NL == 1 ? launch_conv<16, 1, true>(pl.prm, pl.grid, st) : launch_conv<16, 2, true>(pl.prm, pl.grid, st);
   if (pl.bn == 128) return NL == 1 ? launch_conv<128, 1, false>(pl.prm, pl.grid, st) : launch_conv<128, 2, false>(pl.prm, pl.grid, st);
@@ -1063,6 +1106,16 @@ int lspg_debug_read_tensor(lspg_handle h, int id, int limb, uint16_t* dst, int64
   CUDA_TRY(cudaDeviceSynchronize());
   CUDA_TRY(cudaMemcpy(dst, static_cast<uint8_t*>(P->workspace) + P->tensor_off[id] + limb * P->tensor_limb_stride[id], bytes,
                       cudaMemcpyDeviceToHost));
+  return LSPG_OK;
+}
+
+int lspg_debug_read_trace(lspg_handle h, uint64_t* dst, int64_t count) {
+  if (!h || !dst) return fail(LSPG_EINVAL, "null argument");
+  if (!h->trace_buf) return fail(LSPG_ESTATE, "no trace recorded (set LSPG_TRACE_LAYER=<layer index> before the first forward)");
+  if (count != 256 * kTraceSlots) return fail(LSPG_EINVAL, "count must be %d", 256 * kTraceSlots);
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpy(dst, h->trace_buf, sizeof(uint64_t) * count, cudaMemcpyDeviceToHost));
   return LSPG_OK;
 }
 
