@@ -112,6 +112,15 @@ __device__ __forceinline__ void trace_stamp(const ConvParams& p, int slot) {
   if (p.trace != nullptr && slot < kTraceSlots) p.trace[static_cast<size_t>(blockIdx.x) * kTraceSlots + slot] = clock64();
 }
 
+// The MMA-issuing warp only needs the phase and split index of a tile; for the common single-phase, unsplit layer that
+// is (0, 0) without any integer division (the full decode costs several hundred cycles between two tiles).
+__device__ __forceinline__ void decode_tile_zs(const ConvParams& p, int t, int& z, int& split) {
+  if (p.n_phases == 1 && p.n_split == 1) { z = 0; split = 0; return; }
+  split = t / p.tiles_per_split;
+  t -= split * p.tiles_per_split;
+  z = t / (p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles);
+}
+
 __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int t) {
   TileCoord c;
   const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
@@ -285,9 +294,14 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, uint8_t* stg
 #pragma unroll
             for (int l = 0; l < NL; ++l)
 #pragma unroll
-              for (int c16 = 0; c16 < 8; ++c16)
-                rs[l][c16] = pix_ok ? __ldg(reinterpret_cast<const uint4*>(res_row + l * p.res_limb_stride + chunk * kChunk) + c16)
-                                    : make_uint4(0u, 0u, 0u, 0u);
+              for (int c32 = 0; c32 < 4; ++c32) {
+                if (pix_ok) {
+                  ptx::ldg256_nc(res_row + l * p.res_limb_stride + chunk * kChunk + c32 * 16, rs[l][2 * c32], rs[l][2 * c32 + 1]);
+                } else {
+                  rs[l][2 * c32] = make_uint4(0u, 0u, 0u, 0u);
+                  rs[l][2 * c32 + 1] = make_uint4(0u, 0u, 0u, 0u);
+                }
+              }
           }
           uint32_t vv[2][32];
           ptx::tmem_ld_32x32(t_acc + chunk * kChunk, vv[0]);
@@ -309,6 +323,7 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, uint8_t* stg
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
           }
+          uint4 o_prev = make_uint4(0u, 0u, 0u, 0u), ol_prev = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
           for (int piece = 0; piece < 8; ++piece) {          // 16-byte pieces: 8 channels each
             float y[8];
@@ -337,15 +352,23 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, uint8_t* stg
             o.y = pack_bf16x2(y[2], y[3]);
             o.z = pack_bf16x2(y[4], y[5]);
             o.w = pack_bf16x2(y[6], y[7]);
-            if (pix_ok) *reinterpret_cast<uint4*>(out_row + chunk * kChunk + piece * 8) = o;
+            uint4 ol = make_uint4(0u, 0u, 0u, 0u);
             if (NL == 2) {
               const uint32_t oo[4] = {o.x, o.y, o.z, o.w};
               uint32_t lo[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e)
                 lo[e] = pack_bf16x2(y[2 * e] - bf16_lo(oo[e]), y[2 * e + 1] - bf16_hi(oo[e]));
-              if (pix_ok)
-                *reinterpret_cast<uint4*>(out_row + p.out_limb_stride + chunk * kChunk + piece * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+              ol = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+            if (piece & 1) {               // two 16-byte pieces = one 32-byte sector per store
+              if (pix_ok) {
+                ptx::stg256(out_row + chunk * kChunk + (piece - 1) * 8, o_prev, o);
+                if (NL == 2) ptx::stg256(out_row + p.out_limb_stride + chunk * kChunk + (piece - 1) * 8, ol_prev, ol);
+              }
+            } else {
+              o_prev = o;
+              ol_prev = ol;
             }
           }
         }
@@ -693,7 +716,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
     bool b_ready = false;
     int lt = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++lt) {
-      const TileCoord tc = decode_tile(p, t);
+      TileCoord tc;
+      decode_tile_zs(p, t, tc.z, tc.split);
       ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       ptx::tc_fence_after();
       if (lane == 0) trace_stamp(p, 4 + 8 * lt + 0);

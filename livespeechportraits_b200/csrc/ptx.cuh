@@ -32,6 +32,20 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ------------------------------------------------------------------ 256-bit global accesses (sm_100: LDG/STG.256)
+// One access = one full 32-byte sector; with the whole smem/L1 array carved out as shared memory there is almost no L1
+// to merge 16-byte accesses of the same sector, so the epilogue moves whole sectors.
+__device__ __forceinline__ void ldg256_nc(const void* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x),
+               "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+
 // ------------------------------------------------------------------ programmatic dependent launch
 // wait: block until the grids this launch depends on have completed and their writes are visible.
 // launch_dependents: allow the next kernel in the stream to start launching (its prologue overlaps our tail).
