@@ -39,6 +39,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--mode", default="parity", choices=["parity", "fast"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--variant", default="large", choices=["large", "normal"],
+                    help="large = May.yaml (BASELINE.json configs[1], default); normal = Obama1/Nadella/... (configs[2])")
     ap.add_argument("--no-extras", action="store_true", help="skip the fast-mode / single-frame side measurements")
     return ap.parse_args()
 
@@ -146,7 +148,7 @@ def run_reference(args, rank: int):
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": min(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic (seeded weights with the reference init distribution, seeded inputs)",
-        "config": {"workload": f"May.yaml large 512x512, {per_step} frames per step on the host CPU", "variant": VARIANT,
+        "config": {"workload": f"{VARIANT} 512x512, {per_step} frames per step on the host CPU", "variant": VARIANT,
                    "batch": per_step},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                          "sample": f"{steps} steps x {per_step} frames, fp32, torch ATen convs (oracle/f2f_oracle.py)"},
@@ -157,7 +159,10 @@ def run_reference(args, rank: int):
 
 
 def main():
+    global VARIANT, METRIC
     args = parse()
+    VARIANT = args.variant
+    METRIC = f"512x512 frames/sec (Feature2Face_G {VARIANT} / {'May.yaml' if VARIANT == 'large' else 'Obama1.yaml'})"
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -346,6 +351,17 @@ def main():
         err_o = (net.render(fm_pool[0][:1], cand, precision=other).cpu() - O.generator_forward(sd, x0, VARIANT)).abs().max().item()
         extras[f"{other}_mode"] = {"value": B / ms_o * 1e3, "unit": "frames/s", "max_abs_err_vs_oracle": err_o,
                                    "tflops_algorithmic": flops_step / (ms_o / 1e3) / 1e12}
+        # N1: frames leave the GPU as uint8 HWC images (util.tensor2im fused into the tail kernel)
+        img_host = torch.empty((n_clip, H, W, 3), dtype=torch.uint8, pin_memory=True)
+        clip8 = ClipRenderer(net, batch=B, device=dev, uint8=True)
+        clip8.render_clip(fm_host[: B * 2], cand, img_host[: B * 2])
+        torch.cuda.synchronize()
+        t8 = time.perf_counter()
+        clip8.render_clip(fm_host, cand, img_host)
+        torch.cuda.synchronize()
+        dt8 = time.perf_counter() - t8
+        extras["e2e_uint8_images"] = {"value": n_clip / dt8, "unit": "frames/s", "d2h_bytes_per_step": B * H * W * 3,
+                                      "api": "ClipRenderer(uint8=True): lspg_forward_image (tensor2im fused, util/util.py:19-42)"}
         one = fm_pool[0][:1].contiguous()
         ms_1 = timed(lambda: net.render(one, cand), 30)
         extras["single_frame"] = {"value": 1e3 / ms_1, "unit": "frames/s", "ms_per_frame": ms_1, "mode": args.mode,
@@ -364,7 +380,7 @@ def main():
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.mode == "fast" else "bf16 hi+lo split operands (3 tcgen05 MMAs per K step), fp32 accumulate",
             "data": "synthetic (seeded weights with the reference's init distribution - no checkpoint ships; seeded inputs)",
-            "config": {"workload": f"May.yaml (large) 512x512, clip rendered {B} frames per step, "
+            "config": {"workload": f"{'May.yaml (large)' if VARIANT == 'large' else 'Obama1.yaml (normal)'} 512x512, clip rendered {B} frames per step, "
                                    + ("single GPU" if world == 1 else f"frame-sharded over {world} GPUs + NCCL all-gather of the frames"),
                        "variant": VARIANT, "batch": B, "height": H, "width": W, "precision_mode": args.mode,
                        "parallelism": f"dp{world}",

@@ -79,6 +79,14 @@ int lspg_forward(lspg_handle h, const float* feature_map, int64_t fm_bstride, co
                  int64_t cand_bstride, float* out, int batch, int height, int width, void* workspace,
                  size_t workspace_bytes, int mode, void* stream);
 
+/* Same as lspg_forward with the reference's post-processing fused into the last kernel: replaces
+ * util.tensor2im(pred_fake[i]) (util/util.py:19-42, called at demo.py:268) = (x+1)/2*255 in fp32, clip to [0,255],
+ * truncate to uint8, CHW -> HWC.  out_hwc: device uint8 [B,H,W,3].  A quarter of the bytes of the fp32 frame, so the
+ * device->host copy and the multi-GPU all-gather of frames shrink 4x. */
+int lspg_forward_image(lspg_handle h, const float* feature_map, int64_t fm_bstride, const float* cand,
+                       int64_t cand_bstride, uint8_t* out_hwc, int batch, int height, int width, void* workspace,
+                       size_t workspace_bytes, int mode, void* stream);
+
 /* Replaces nothing in the reference (module garbage collection). */
 int lspg_destroy(lspg_handle h);
 

@@ -43,6 +43,7 @@ struct alignas(64) ConvParams {
   const float* scale;        // folded BatchNorm (or 1/0), [Cout_pad]
   const float* shift;
   float* out_f32;            // tail only: fp32 NCHW [B, 3, 2*hs, 2*ws]
+  uint8_t* out_u8;           // tail only, optional: uint8 HWC image [B, 2*hs, 2*ws, 3] = util.tensor2im fused (then out_f32 is unused)
   __nv_bfloat16* out_ptr;         // output tensor (NHWC), limb 0; written directly by the epilogue
   long long out_limb_stride;      // elements between limbs
   int32_t out_channels, out_up;   // out_up: the sampling grid is the source of a folded x2 upsample (phase tc.z -> (2y+py, 2x+px))
@@ -74,6 +75,7 @@ struct alignas(64) ConvParams {
   // partial[tile_index][128][BN]; splitk_reduce_kernel sums the splits and applies the epilogue.
   int32_t n_split, split_len, tiles_per_split;
   float* partial;
+  int* split_counter;            // [tiles_per_split] arrival counters (zero between forwards); null = two-pass (finisher kernel)
   unsigned long long* trace;     // debug: per-CTA clock64 stamps (null in production), see kTraceSlots
   int32_t tap_rotate;            // patch mode: tile (x,y) dependent rotation of the tap order, so that concurrently
                                  // running CTAs do not all request the same weight tile from L2 at the same time
@@ -162,6 +164,7 @@ template <int BN, int NL, bool TAIL, int NSTG, bool STACK>
 __device__ __forceinline__ void epilogue_warps(const ConvParams& p, uint8_t* stg_base, float* s_scale0, float* /*unused*/,
                                                uint64_t* tfull_bar, uint64_t* tempty_bar, uint64_t* stg_bar,
                                                uint32_t tmem_base, int warp, int lane) {
+  int* fix_flag = reinterpret_cast<int*>(stg_bar + 2) + 1;   // smem word right after the TMEM-address slot
   using Cfg = StgCfg<NSTG>;
     // ===================================================================== epilogue (warps 2..5)
     ptx::pdl_wait();   // residual reads, output / split-K partial writes must not overtake the previous kernel
@@ -187,6 +190,7 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, uint8_t* stg
         s_shift[i] = p.shift[tc.nt * BN + i];
       }
       const bool split_mode = !TAIL && p.n_split > 1;
+      bool fixup = false;
       ptx::named_bar_sync(1, kEpiThreads);
 
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
@@ -210,11 +214,35 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, uint8_t* stg
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+        const uint32_t* v_ = v;
         const int tw = row & ((1 << p.tw_log2) - 1);
         const int th = (row >> p.tw_log2) & ((1 << p.th_log2) - 1);
         const int nb = row >> (p.tw_log2 + p.th_log2);
         const int n = tc.n0 + nb, y = tc.y0 + th, x = tc.x0 + tw;
-        if (n < p.batch && y < p.hs && x < p.ws) {
+        if (n < p.batch && y < p.hs && x < p.ws && p.out_u8 != nullptr) {
+          // fused util/util.py:tensor2im (reference lines 33-42): (x + 1) / 2 * 255 in fp32, clip to [0,255], truncate to
+          // uint8, CHW -> HWC.  This thread owns output pixels (2y+py, 2x+px): per py, 2 pixels x 3 channels = 6 bytes.
+          const int oh = 2 * p.hs, ow = 2 * p.ws;
+#pragma unroll
+          for (int py = 0; py < 2; ++py) {
+            uint8_t b[6];
+#pragma unroll
+            for (int px = 0; px < 2; ++px)
+#pragma unroll
+              for (int c = 0; c < 3; ++c) {
+                const int col = (py * 2 + px) * 3 + c;
+                const float v = tanhf(__uint_as_float(v_[col]) * s_scale[col] + s_shift[col]);
+                float u = __fmul_rn(__fmul_rn(__fadd_rn(v, 1.0f), 0.5f), 255.0f);
+                u = fminf(fmaxf(u, 0.0f), 255.0f);
+                b[px * 3 + c] = static_cast<uint8_t>(static_cast<int>(u));
+              }
+            uint8_t* dst = p.out_u8 + ((static_cast<size_t>(n) * oh + (2 * y + py)) * ow + 2 * x) * 3;
+            uint16_t* d16 = reinterpret_cast<uint16_t*>(dst);          // 6-byte aligned: 2x * 3 is even
+            d16[0] = static_cast<uint16_t>(b[0] | (b[1] << 8));
+            d16[1] = static_cast<uint16_t>(b[2] | (b[3] << 8));
+            d16[2] = static_cast<uint16_t>(b[4] | (b[5] << 8));
+          }
+        } else if (n < p.batch && y < p.hs && x < p.ws) {
           const int oh = 2 * p.hs, ow = 2 * p.ws;
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
@@ -232,7 +260,7 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, uint8_t* stg
         }
       } else if constexpr (!TAIL) {
        if (split_mode) {
-        // ---- split-K partial: raw fp32 accumulator rows -> partial[t][row][BN]; the reduce kernel finishes the job
+        // ---- split-K partial: raw fp32 accumulator rows -> partial[t][row][BN]
         float* dst = p.partial + (static_cast<size_t>(t) * kTileM + row) * BN;
 #pragma unroll 1
         for (int c32 = 0; c32 < BN / 32; ++c32) {
@@ -255,7 +283,55 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, uint8_t* stg
           for (int e = 0; e < 8; ++e)
             *reinterpret_cast<uint4*>(dst + c32 * 32 + e * 4) = make_uint4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
         }
-      } else {
+        if (p.split_counter != nullptr) {
+          // In-kernel finish: the CTA that publishes the LAST partial of an output tile sums all of them (in split
+          // order, so the result does not depend on which CTA that is) and runs the regular epilogue below.
+          __threadfence();
+          ptx::named_bar_sync(2, kEpiThreads);
+          if (leader) {
+            const int tile_id = t - tc.split * p.tiles_per_split;
+            const int old = atomicAdd(p.split_counter + tile_id, 1);
+            const int last = (old == p.n_split - 1) ? 1 : 0;
+            if (last) p.split_counter[tile_id] = 0;          // ready for the next forward
+            *fix_flag = last;
+          }
+          ptx::named_bar_sync(3, kEpiThreads);
+          fixup = (*fix_flag != 0);
+          __threadfence();
+          if (fixup) {
+            // cooperative, coalesced reduction of the tile: thread i owns float4 i, i+128, ... ; splits are added in
+            // order 0,1,2,... (deterministic), four loads in flight per accumulator; the sum replaces split 0's partial
+            float* base = p.partial + static_cast<size_t>(t - tc.split * p.tiles_per_split) * kTileM * BN;
+            const size_t split_stride = static_cast<size_t>(p.tiles_per_split) * kTileM * BN;
+            auto ldcg = [](const float* q) {
+              float4 a;
+              asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(q));
+              return a;
+            };
+            for (int k = etid; k < kTileM * BN / 4; k += kEpiThreads) {
+              float* q = base + static_cast<size_t>(k) * 4;
+              float4 acc4 = ldcg(q);
+              int sp = 1;
+              for (; sp + 4 <= p.n_split; sp += 4) {
+                const float4 a0 = ldcg(q + (sp + 0) * split_stride), a1 = ldcg(q + (sp + 1) * split_stride);
+                const float4 a2 = ldcg(q + (sp + 2) * split_stride), a3 = ldcg(q + (sp + 3) * split_stride);
+                acc4.x += a0.x; acc4.y += a0.y; acc4.z += a0.z; acc4.w += a0.w;
+                acc4.x += a1.x; acc4.y += a1.y; acc4.z += a1.z; acc4.w += a1.w;
+                acc4.x += a2.x; acc4.y += a2.y; acc4.z += a2.z; acc4.w += a2.w;
+                acc4.x += a3.x; acc4.y += a3.y; acc4.z += a3.z; acc4.w += a3.w;
+              }
+              for (; sp < p.n_split; ++sp) {
+                const float4 a0 = ldcg(q + sp * split_stride);
+                acc4.x += a0.x; acc4.y += a0.y; acc4.z += a0.z; acc4.w += a0.w;
+              }
+              *reinterpret_cast<float4*>(q) = acc4;
+            }
+            __threadfence();
+            ptx::named_bar_sync(2, kEpiThreads);
+          }
+        }
+       }
+       if (!split_mode || fixup) {
         // ---- regular: scale/shift (+ residual) + ReLU, bf16 (hi, lo), written straight to the NHWC output.
         // Each thread owns one pixel: it reads its residual row and writes its output row (64 channels = 128
         // contiguous bytes per chunk and limb) with plain 16-byte global accesses.  No smem staging and no TMA
@@ -304,6 +380,21 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, uint8_t* stg
               }
           }
           uint32_t vv[2][32];
+          if (fixup) {
+            // the summed tile was written back to split 0's slot by the cooperative pass above
+            const float* src0 = p.partial + (static_cast<size_t>(t - tc.split * p.tiles_per_split) * kTileM + row) * BN + chunk * kChunk;
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                float4 a;
+                asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(src0 + hf * 32 + e * 4));
+                vv[hf][4 * e] = __float_as_uint(a.x);
+                vv[hf][4 * e + 1] = __float_as_uint(a.y);
+                vv[hf][4 * e + 2] = __float_as_uint(a.z);
+                vv[hf][4 * e + 3] = __float_as_uint(a.w);
+              }
+          } else {
           ptx::tmem_ld_32x32(t_acc + chunk * kChunk, vv[0]);
           ptx::tmem_ld_32x32(t_acc + chunk * kChunk + 32, vv[1]);
           if constexpr (STACK) {
@@ -322,6 +413,7 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, uint8_t* stg
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+          }
           }
           uint4 o_prev = make_uint4(0u, 0u, 0u, 0u), ol_prev = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll

@@ -103,9 +103,9 @@ struct PlanLayer {
 };
 
 struct IoKey {
-  const float* fm; int64_t fm_bstride; const float* cand; int64_t cand_bstride; float* out;
+  const float* fm; int64_t fm_bstride; const float* cand; int64_t cand_bstride; void* out; int u8;
   bool operator==(const IoKey& o) const {
-    return fm == o.fm && fm_bstride == o.fm_bstride && cand == o.cand && cand_bstride == o.cand_bstride && out == o.out;
+    return fm == o.fm && fm_bstride == o.fm_bstride && cand == o.cand && cand_bstride == o.cand_bstride && out == o.out && u8 == o.u8;
   }
 };
 
@@ -480,10 +480,12 @@ Geo layer_geo(const lspg_ctx* h, const Layer& L, int B, int H, int W) {
   return g;
 }
 
+constexpr size_t kCounterBytes = 4096;     // split-K arrival counters (one int per output tile of the layer in flight)
+
 size_t scratch_bytes(const lspg_ctx* h, int B, int H, int W) {
   size_t m = 0;
   for (const auto& L : h->layers) m = std::max(m, layer_geo(h, L, B, H, W).partial_bytes);
-  return align_up(m, 1024);
+  return kCounterBytes + align_up(m, 1024);
 }
 
 size_t workspace_bytes(const lspg_ctx* h, int B, int H, int W, int mode) {
@@ -599,6 +601,7 @@ int build_plan(lspg_ctx* h, Plan* P, int B, int H, int W, int mode, void* worksp
   }
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   uint8_t* ws_scratch = ws + align_up(off, 1024);
+  CUDA_TRY(cudaMemset(ws_scratch, 0, kCounterBytes));      // counters return to zero at the end of every layer that uses them
   for (const Layer& L : h->layers) {
     PlanLayer pl;
     ConvParams& p = pl.prm;
@@ -640,8 +643,14 @@ int build_plan(lspg_ctx* h, Plan* P, int B, int H, int W, int mode, void* worksp
     p.tiles_per_split = g.tiles_per_split;
     p.n_split = g.n_split; p.split_len = g.split_len;
     p.total_tiles = g.tiles_per_split * g.n_split;
-    p.partial = reinterpret_cast<float*>(ws_scratch);
-    pl.split = g.n_split > 1;
+    p.partial = reinterpret_cast<float*>(ws_scratch + kCounterBytes);
+    // Measured on B200: letting the last-arriving CTA sum the partials in-kernel (LSPG_SPLITK_FIXUP=1) is slower than a
+    // separate finisher kernel (B=1: 2.19 vs 1.44 ms per frame) - one CTA's 128 threads reduce a tile far more slowly
+    // than a grid of them - so the two-pass scheme is the default.
+    static const bool two_pass = getenv("LSPG_SPLITK_FIXUP") == nullptr;
+    const bool fix_in_kernel = !two_pass && g.n_split > 1 && static_cast<size_t>(g.tiles_per_split) * sizeof(int) <= kCounterBytes;
+    p.split_counter = fix_in_kernel ? reinterpret_cast<int*>(ws_scratch) : nullptr;
+    pl.split = g.n_split > 1 && !fix_in_kernel;      // two-pass: a finisher kernel follows
     p.n_taps = L.n_taps; p.n_src = L.n_src;
     p.chunks[0] = L.cin[0] / 64; p.chunks[1] = L.n_src == 2 ? L.cin[1] / 64 : 0;
     p.relu = L.relu; p.has_res = L.res >= 0 ? 1 : 0;
@@ -843,7 +852,10 @@ int enqueue_forward(lspg_ctx* h, Plan* P, const IoKey& io, cudaStream_t st, bool
   // 2. conv stack
   for (size_t i = 0; i < h->layers.size(); ++i) {
     PlanLayer& pl = P->layers[i];
-    if (h->layers[i].kind == K_TAIL) pl.prm.out_f32 = io.out;
+    if (h->layers[i].kind == K_TAIL) {
+      pl.prm.out_f32 = io.u8 ? nullptr : static_cast<float*>(io.out);
+      pl.prm.out_u8 = io.u8 ? static_cast<uint8_t*>(io.out) : nullptr;
+    }
     if ((rc = launch_layer(pl, h->layers[i].kind, NL, st))) return rc;
     if (pl.split) {
       CUDA_TRY(launch_pdl(splitk_reduce_kernel, dim3(pl.red_blocks), dim3(128), 0, st, pl.red));
@@ -974,9 +986,9 @@ int lspg_workspace_bytes(lspg_handle h, int batch, int height, int width, int mo
   return LSPG_OK;
 }
 
-int lspg_forward(lspg_handle h, const float* feature_map, int64_t fm_bstride, const float* cand, int64_t cand_bstride,
-                 float* out, int batch, int height, int width, void* workspace, size_t workspace_bytes_in, int mode,
-                 void* stream) {
+static int forward_impl(lspg_handle h, const float* feature_map, int64_t fm_bstride, const float* cand, int64_t cand_bstride,
+                        void* out, int out_is_u8, int batch, int height, int width, void* workspace, size_t workspace_bytes_in,
+                        int mode, void* stream) {
   if (!h) return fail(LSPG_EINVAL, "null handle");
   if (h->device < 0) return fail(LSPG_ENODEV, "host-only handle: lspg_forward needs an sm_100 device (no CPU path exists)");
   if (!h->weights_loaded) return fail(LSPG_ESTATE, "lspg_load_weights has not been called");
@@ -1002,7 +1014,7 @@ int lspg_forward(lspg_handle h, const float* feature_map, int64_t fm_bstride, co
   }
   Plan* P = it->second.get();
   h->last_plan = P;
-  IoKey io{feature_map, fm_bstride, cand, cand_bstride, out};
+  IoKey io{feature_map, fm_bstride, cand, cand_bstride, out, out_is_u8};
   static const bool no_graph = getenv("LSPG_NO_GRAPH") != nullptr;
   static const bool debug_sync = getenv("LSPG_DEBUG_SYNC") != nullptr;   // per-layer sync + error attribution (bring-up)
   if (no_graph || debug_sync || h->profiling) return enqueue_forward(h, P, io, st, debug_sync, h->profiling);
@@ -1034,6 +1046,20 @@ int lspg_forward(lspg_handle h, const float* feature_map, int64_t fm_bstride, co
   P->graphs.push_back(ge);
   CUDA_TRY(cudaGraphLaunch(ge.exec, st));
   return LSPG_OK;
+}
+
+int lspg_forward(lspg_handle h, const float* feature_map, int64_t fm_bstride, const float* cand, int64_t cand_bstride,
+                 float* out, int batch, int height, int width, void* workspace, size_t workspace_bytes_in, int mode,
+                 void* stream) {
+  return forward_impl(h, feature_map, fm_bstride, cand, cand_bstride, out, 0, batch, height, width, workspace,
+                      workspace_bytes_in, mode, stream);
+}
+
+int lspg_forward_image(lspg_handle h, const float* feature_map, int64_t fm_bstride, const float* cand, int64_t cand_bstride,
+                       uint8_t* out_hwc, int batch, int height, int width, void* workspace, size_t workspace_bytes_in,
+                       int mode, void* stream) {
+  return forward_impl(h, feature_map, fm_bstride, cand, cand_bstride, out_hwc, 1, batch, height, width, workspace,
+                      workspace_bytes_in, mode, stream);
 }
 
 // ---------------------------------------------------------------------------------------- introspection

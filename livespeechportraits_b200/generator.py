@@ -164,8 +164,14 @@ class Feature2Face_G(nn.Module):
             self._workspaces[key] = ws
         return ws
 
+    def render_image(self, feature_map: torch.Tensor, cand_image: Optional[torch.Tensor], out: Optional[torch.Tensor] = None,
+                     precision: Optional[str] = None) -> torch.Tensor:
+        """``render`` + ``util.tensor2im`` (util/util.py:19-42) fused into the last kernel: uint8 ``[B,H,W,3]`` images
+        (``(x+1)/2*255``, clip, truncate, HWC) instead of fp32 ``[B,3,H,W]`` - what demo.py:268 builds per frame."""
+        return self.render(feature_map, cand_image, out=out, precision=precision, _uint8=True)
+
     def render(self, feature_map: torch.Tensor, cand_image: Optional[torch.Tensor], out: Optional[torch.Tensor] = None,
-               precision: Optional[str] = None) -> torch.Tensor:
+               precision: Optional[str] = None, _uint8: bool = False) -> torch.Tensor:
         """Fused ``torch.cat([feature_map, cand_image], 1)`` + generator (feature2face_model.py:231-233).
 
         ``cand_image`` may have batch 1 (broadcast over the frames, as demo.py:266 reuses one candidate set).
@@ -198,13 +204,15 @@ class Feature2Face_G(nn.Module):
             hold = (fm, cd)
         mode = _lib.LSPG_MODE[precision or self.precision]
         ws = self._workspace(b, h, w, mode)
+        oshape, odtype = ((b, h, w, self.out_nc), torch.uint8) if _uint8 else ((b, self.out_nc, h, w), torch.float32)
         if out is None:
-            out = torch.empty((b, self.out_nc, h, w), dtype=torch.float32, device=feature_map.device)
-        elif out.shape != (b, self.out_nc, h, w) or out.dtype != torch.float32 or not out.is_contiguous():
-            raise ValueError("out must be a contiguous fp32 [B,3,H,W] tensor")
+            out = torch.empty(oshape, dtype=odtype, device=feature_map.device)
+        elif tuple(out.shape) != oshape or out.dtype != odtype or not out.is_contiguous():
+            raise ValueError(f"out must be a contiguous {odtype} tensor of shape {oshape}")
         stream = torch.cuda.current_stream(feature_map.device).cuda_stream
-        _lib.check(self._lib.lspg_forward(self._handle, fm_ptr, fm_stride, cand_ptr, cand_stride, out.data_ptr(), b, h, w,
-                                          ws.data_ptr(), ws.numel(), mode, stream))
+        fn = self._lib.lspg_forward_image if _uint8 else self._lib.lspg_forward
+        _lib.check(fn(self._handle, fm_ptr, fm_stride, cand_ptr, cand_stride, out.data_ptr(), b, h, w,
+                      ws.data_ptr(), ws.numel(), mode, stream))
         del hold
         return out
 

@@ -14,8 +14,11 @@ import torch
 
 
 class ClipRenderer:
-    def __init__(self, net, batch: int = 8, device: Optional[torch.device] = None, precision: Optional[str] = None):
+    def __init__(self, net, batch: int = 8, device: Optional[torch.device] = None, precision: Optional[str] = None,
+                 uint8: bool = False):
+        """``uint8=True``: frames leave the GPU as uint8 HWC images (util.tensor2im fused into the last kernel)."""
         self.net = net
+        self.uint8 = uint8
         self.batch = int(batch)
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         self.precision = precision
@@ -28,7 +31,8 @@ class ClipRenderer:
     def _staging(self, h: int, w: int):
         if self._fm is None or self._fm[0].shape[-2:] != (h, w):
             self._fm = [torch.empty((self.batch, 1, h, w), dtype=torch.float32, device=self.device) for _ in range(2)]
-            self._out = [torch.empty((self.batch, 3, h, w), dtype=torch.float32, device=self.device) for _ in range(2)]
+            oshape, odt = ((self.batch, h, w, 3), torch.uint8) if self.uint8 else ((self.batch, 3, h, w), torch.float32)
+            self._out = [torch.empty(oshape, dtype=odt, device=self.device) for _ in range(2)]
         return self._fm, self._out
 
     def render_clip(self, feature_maps_host: torch.Tensor, cand_device: torch.Tensor, out_host: torch.Tensor) -> torch.Tensor:
@@ -36,8 +40,8 @@ class ClipRenderer:
         candidates once per clip), ``out_host`` [N,3,H,W] fp32 (pinned).  Returns ``out_host`` after the last copy
         has landed (the only host synchronisation of the call)."""
         n, _, h, w = feature_maps_host.shape
-        if out_host.shape != (n, 3, h, w):
-            raise ValueError("out_host must be [N,3,H,W]")
+        if tuple(out_host.shape) != ((n, h, w, 3) if self.uint8 else (n, 3, h, w)):
+            raise ValueError("out_host must be [N,3,H,W] fp32 (or [N,H,W,3] uint8 with uint8=True)")
         if not (feature_maps_host.is_pinned() and out_host.is_pinned()):
             raise ValueError("host buffers must be pinned (torch.empty(..., pin_memory=True)) for asynchronous copies")
         fm_dev, out_dev = self._staging(h, w)
@@ -61,7 +65,7 @@ class ClipRenderer:
                 if d2h_done[j] is not None:
                     self._compute.wait_event(d2h_done[j])        # previous frames of this buffer are on the host
                 cd = cand_device[off:off + ln] if per_frame_cand else cand_device[:1]
-                self.net.render(fm_dev[j][:ln], cd, out=out_dev[j][:ln], precision=self.precision)
+                self.net.render(fm_dev[j][:ln], cd, out=out_dev[j][:ln], precision=self.precision, _uint8=self.uint8)
                 ev = torch.cuda.Event()
                 ev.record(self._compute)
                 comp_done[j] = ev

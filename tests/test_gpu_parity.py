@@ -168,3 +168,35 @@ def test_weight_reload_and_dataparallel_wrap():
         wrapped.load_state_dict({"module." + k: v for k, v in sd.items()}, strict=False)
         out = wrapped(x.cuda()).cpu()
         assert (out - O.generator_forward(sd, x, "normal")).abs().max().item() <= TOL
+
+
+def test_fused_tensor2im_uint8_output():
+    """lspg_forward_image = generator + util.tensor2im (util/util.py:19-42) in the tail kernel's epilogue."""
+    net, sd = get_net("normal", "B")
+    fm, cand = O.make_inputs(2, 256, 256, seed=4)
+    x = torch.cat([fm, cand], 1)
+    f32 = net(x.cuda())
+    u8 = net.render_image(x.cuda(), None)
+    assert u8.shape == (2, 256, 256, 3) and u8.dtype == torch.uint8
+    # identical arithmetic to applying the reference post-processing to the fp32 frames of the same kernels: bit-exact
+    assert np.array_equal(u8.cpu().numpy(), O.tensor2im(f32.cpu()))
+    # against the oracle's frames: the fp32 values differ by <= 1e-3, i.e. at most one grey level where a value sits on an
+    # integer boundary
+    ref = O.tensor2im(O.generator_forward(sd, x, "normal"))
+    d = np.abs(u8.cpu().numpy().astype(np.int16) - ref.astype(np.int16))
+    assert d.max() <= 1 and (d != 0).mean() < 0.02
+
+
+def test_clip_renderer_pipeline_matches_direct_calls():
+    from livespeechportraits_b200.pipeline import ClipRenderer
+    net, _ = get_net("normal", "B")
+    fm, cand = O.make_inputs(5, 256, 256, seed=6)
+    fm_host = fm.pin_memory()
+    direct = net.render(fm.cuda(), cand[:1].cuda()).cpu()
+    out_host = torch.empty((5, 3, 256, 256), dtype=torch.float32).pin_memory()
+    ClipRenderer(net, batch=2).render_clip(fm_host, cand[:1].cuda(), out_host)     # ragged last batch of 1
+    assert (out_host - direct).abs().max().item() <= 2e-5
+    img_host = torch.empty((5, 256, 256, 3), dtype=torch.uint8).pin_memory()
+    ClipRenderer(net, batch=2, uint8=True).render_clip(fm_host, cand[:1].cuda(), img_host)
+    d = np.abs(img_host.numpy().astype(np.int16) - O.tensor2im(direct).astype(np.int16))
+    assert d.max() <= 1

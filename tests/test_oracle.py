@@ -80,3 +80,17 @@ def test_restatement_equals_live_reference_under_its_own_init(variant):
         ref = net(x)
     mine = O.generator_forward(sd, x, variant)
     assert (ref - mine).abs().max().item() <= 1e-6
+
+
+def test_tensor2im_restatement():
+    g = torch.Generator().manual_seed(9)
+    x = torch.tanh(torch.randn(2, 3, 16, 16, generator=g) * 2)
+    x[0, 0, 0, 0], x[0, 1, 0, 0], x[0, 2, 0, 0] = -1.0, 1.0, 0.0        # boundary values: 0, 255, 127
+    u = O.tensor2im(x)
+    assert u.shape == (2, 16, 16, 3) and u.dtype == np.uint8
+    assert tuple(u[0, 0, 0]) == (0, 255, 127)
+    if O.reference_available():
+        O.reference_generator("normal")                                   # puts the reference on sys.path
+        from util import util as ref_util  # type: ignore
+        for i in range(2):
+            assert np.array_equal(ref_util.tensor2im(x[i]), u[i])         # util/util.py:19-42
