@@ -160,7 +160,7 @@ struct StgCfg {
 // STACK (parity mode of the patch kernel): the accumulator of a tile is 2*BN columns wide - columns [0,BN) hold
 // A_hi*B_hi + A_lo*B_hi, columns [BN,2BN) hold A_hi*B_lo (one N=2BN MMA over the stacked [B_hi;B_lo] tile) - and the
 // epilogue adds the two halves.
-template <int BN, int NL, bool TAIL, int NSTG, bool STACK>
+template <int BN, int NL, bool TAIL, int NSTG, bool STACK, bool PAIR = false>
 __device__ __forceinline__ void epilogue_warps(const ConvParams& p, uint8_t* stg_base, float* s_scale0, float* /*unused*/,
                                                uint64_t* tfull_bar, uint64_t* tempty_bar, uint64_t* stg_bar,
                                                uint32_t tmem_base, int warp, int lane) {
@@ -213,7 +213,7 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, uint8_t* stg
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+        if (lane == 0) { if constexpr (PAIR) ptx::mbar_arrive_cluster(&tempty_bar[acc], 0); else ptx::mbar_arrive(&tempty_bar[acc]); }
         const uint32_t* v_ = v;
         const int tw = row & ((1 << p.tw_log2) - 1);
         const int th = (row >> p.tw_log2) & ((1 << p.th_log2) - 1);
@@ -277,7 +277,7 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, uint8_t* stg
           if (c32 == BN / 32 - 1) {
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+            if (lane == 0) { if constexpr (PAIR) ptx::mbar_arrive_cluster(&tempty_bar[acc], 0); else ptx::mbar_arrive(&tempty_bar[acc]); }
           }
 #pragma unroll
           for (int e = 0; e < 8; ++e)
@@ -412,7 +412,7 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, uint8_t* stg
             // accumulator fully drained into registers: hand the TMEM buffer back to the MMA warp
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+            if (lane == 0) { if constexpr (PAIR) ptx::mbar_arrive_cluster(&tempty_bar[acc], 0); else ptx::mbar_arrive(&tempty_bar[acc]); }
           }
           }
           uint4 o_prev = make_uint4(0u, 0u, 0u, 0u), ol_prev = make_uint4(0u, 0u, 0u, 0u);
@@ -874,6 +874,195 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
   }
 }
 
+
+// ====================================================================================================
+// CTA-pair variant (cta_group::2) of the patch kernel for the wide layers (N tile 128 or 256).
+// The two CTAs of a cluster own neighbouring M tiles of the same N tile.  One tcgen05.mma.cta_group::2 (M = 256,
+// issued by the leader only) multiplies both CTAs' A patches with a B tile of which each CTA stores - and fetches -
+// only half the rows; each CTA's 128 accumulator lanes live in its own TMEM and are drained by its own epilogue warps.
+// Per SM this halves the B operand reads and the B fill traffic of shared memory, which is what bounds the
+// single-CTA kernel, halves the L2->SM weight traffic and doubles the ring depth per byte.
+// PARITY (NL = 2) issues hi*hi, hi*lo, lo*hi as three N = BN MMAs (B_hi and B_lo are each split across the pair).
+// ====================================================================================================
+template <int BN, int NL>
+struct PairCfg {
+  static constexpr int kBHalf = (BN / 2) * 128;                   // bytes of this CTA's half of one B tile
+  static constexpr int kAStage = NL * kPatchStride;
+  static constexpr int kBStage = NL * kBHalf;                     // one tap per stage
+  static constexpr int kAStages = 2;
+  static constexpr int kAux = 5120;
+  static constexpr int kAvail = kSmemBudget - 1024 - kAux - kAStages * kAStage;
+  static constexpr int kBStagesRaw = kAvail / kBStage;
+  static constexpr int kBStages = kBStagesRaw > 12 ? 12 : kBStagesRaw;
+  static constexpr int kSmemBytes = 1024 + kAStages * kAStage + kBStages * kBStage + kAux;
+  static constexpr int kTmemCols = 2 * BN;
+  static_assert(BN == 128 || BN == 256, "pair kernel: N tile 128 or 256");
+  static_assert(kTmemCols <= 512, "TMEM has 512 columns");
+  static_assert(kBStages >= 3, "B ring too shallow");
+  static_assert(4 * BN * 4 + (2 * 12 + 2 * 2 + 8) * 8 <= kAux, "aux region too small");
+};
+
+template <int BN, int NL>
+__global__ void __launch_bounds__(kThreads, 1) conv_pair_kernel(const __grid_constant__ ConvParams p) {
+  using Cfg = PairCfg<BN, NL>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a_ring = smem;
+  uint8_t* b_ring = a_ring + Cfg::kAStages * Cfg::kAStage;
+  uint8_t* aux = b_ring + Cfg::kBStages * Cfg::kBStage;
+  float* s_scale = reinterpret_cast<float*>(aux);
+  float* s_shift = s_scale + BN;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(aux + 4 * BN * 4);
+  uint64_t* afull_bar = bars;                               // [kAStages]  (used in the leader)
+  uint64_t* aempty_bar = afull_bar + Cfg::kAStages;         // [kAStages]
+  uint64_t* bfull_bar = aempty_bar + Cfg::kAStages;         // [kBStages]  (used in the leader)
+  uint64_t* bempty_bar = bfull_bar + Cfg::kBStages;         // [kBStages]
+  uint64_t* tfull_bar = bempty_bar + Cfg::kBStages;         // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;                     // [2]        (used in the leader: 8 arrivals)
+  uint64_t* stg_bar = tempty_bar + 2;                       // [2] unused (layout shared with the other kernels)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stg_bar + 2);
+
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t crank = ptx::cluster_ctarank();
+  const bool leader_cta = (crank == 0);
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 4; ++i) ptx::prefetch_tmap(&p.a[i]);
+    ptx::prefetch_tmap(&p.w);
+    for (int i = 0; i < Cfg::kAStages; ++i) { ptx::mbar_init(&afull_bar[i], 1); ptx::mbar_init(&aempty_bar[i], 1); }
+    for (int i = 0; i < Cfg::kBStages; ++i) { ptx::mbar_init(&bfull_bar[i], 1); ptx::mbar_init(&bempty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&tfull_bar[i], 1);
+      ptx::mbar_init(&tempty_bar[i], 8);       // 4 epilogue warps of each CTA of the pair
+      ptx::mbar_init(&stg_bar[i], 1);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc_pair(tmem_slot, Cfg::kTmemCols);
+    ptx::tmem_relinquish_pair();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  ptx::pdl_launch_dependents();
+
+  int kb_per_tap = 0;
+  for (int s = 0; s < p.n_src; ++s) kb_per_tap += p.chunks[s];
+  const int patch_bytes = p.patch_w * p.patch_h * 128;
+  constexpr uint16_t kMask = 0x3;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer (both CTAs)
+    ptx::pdl_wait();
+    int ia = 0, ib = 0;
+    uint32_t pha = 0, phb = 0;
+    int a_tile = blockIdx.x, a_ci = 0;
+    auto issue_a = [&]() {
+      if (a_tile >= p.total_tiles) return;
+      const TileCoord tc = decode_tile(p, a_tile);
+      const int s = (a_ci < p.chunks[0]) ? 0 : 1;
+      const int c = (s == 0) ? a_ci : a_ci - p.chunks[0];
+      ptx::mbar_wait(&aempty_bar[ia], pha ^ 1);
+      if (ptx::elect_one()) {
+        if (leader_cta) ptx::mbar_expect_tx(&afull_bar[ia], 2 * NL * patch_bytes);     // both CTAs' patches
+#pragma unroll
+        for (int l = 0; l < NL; ++l)
+          ptx::tma_load_5d_pair(&p.a[s], &afull_bar[ia], a_ring + ia * Cfg::kAStage + l * kPatchStride, c * kChunk,
+                                tc.x0 + p.patch_dx0[tc.z], tc.y0 + p.patch_dy0[tc.z], tc.n0, l);
+      }
+      __syncwarp();
+      if (++ia == Cfg::kAStages) { ia = 0; pha ^= 1; }
+      if (++a_ci == kb_per_tap) { a_ci = 0; a_tile += gridDim.x; }
+    };
+    issue_a();
+    const int a_after = (p.n_taps > 2) ? 2 : p.n_taps - 1;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      const TileCoord tc = decode_tile(p, t);
+      for (int ci = 0; ci < kb_per_tap; ++ci) {
+        for (int tap = 0; tap < p.n_taps; ++tap) {
+          ptx::mbar_wait(&bempty_bar[ib], phb ^ 1);
+          if (ptx::elect_one()) {
+            uint8_t* st = b_ring + ib * Cfg::kBStage;
+            if (leader_cta) ptx::mbar_expect_tx(&bfull_bar[ib], 2 * Cfg::kBStage);    // both halves
+#pragma unroll
+            for (int l = 0; l < NL; ++l)     // this CTA's half of the tile: rows [crank*BN/2, +BN/2)
+              ptx::tma_load_4d_pair(&p.w, &bfull_bar[ib], st + l * Cfg::kBHalf, ci * kChunk,
+                                    tc.nt * BN + static_cast<int>(crank) * (BN / 2), tap, l * p.n_phases + tc.z);
+          }
+          __syncwarp();
+          if (++ib == Cfg::kBStages) { ib = 0; phb ^= 1; }
+          if (tap == a_after) issue_a();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer (leader CTA only)
+    if (leader_cta) {
+      int ia = 0, ib = 0;
+      uint32_t pha = 0, phb = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      const uint32_t sbo = static_cast<uint32_t>(p.patch_w) * 128u;
+      bool b_ready = false;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        int z, split;
+        decode_tile_zs(p, t, z, split);
+        ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int ci = 0; ci < kb_per_tap; ++ci) {
+          ptx::mbar_wait(&afull_bar[ia], pha);
+          const uint32_t a0 = ptx::smem_u32(a_ring + ia * Cfg::kAStage);
+          for (int tap = 0; tap < p.n_taps; ++tap) {
+            if (!b_ready) ptx::mbar_wait(&bfull_bar[ib], phb);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+              const uint32_t b0 = ptx::smem_u32(b_ring + ib * Cfg::kBStage);
+              const uint32_t a_hi_addr = a0 + static_cast<uint32_t>(p.tap_row[z][tap]) * 128u;
+              const uint64_t a_hi = umma_desc_sw128_strided(a_hi_addr, sbo, false);
+              const uint64_t b_hi = ptx::umma_desc_sw128(b0);
+#pragma unroll
+              for (int k = 0; k < kChunk / 16; ++k) {
+                const uint32_t accum = (ci > 0 || tap > 0 || k > 0) ? 1u : 0u;
+                ptx::umma_f16_pair(d_tmem, a_hi + 2 * k, b_hi + 2 * k, p.idesc, accum);
+                if (NL == 2) {
+                  const uint64_t a_lo = umma_desc_sw128_strided(a_hi_addr + kPatchStride, sbo, false);
+                  const uint64_t b_lo = ptx::umma_desc_sw128(b0 + Cfg::kBHalf);
+                  ptx::umma_f16_pair(d_tmem, a_hi + 2 * k, b_lo + 2 * k, p.idesc, 1u);
+                  ptx::umma_f16_pair(d_tmem, a_lo + 2 * k, b_hi + 2 * k, p.idesc, 1u);
+                }
+              }
+              ptx::umma_commit_pair(&bempty_bar[ib], kMask);
+              if (tap == p.n_taps - 1) {
+                ptx::umma_commit_pair(&aempty_bar[ia], kMask);
+                if (ci == kb_per_tap - 1) ptx::umma_commit_pair(&tfull_bar[acc], kMask);
+              }
+            }
+            __syncwarp();
+            if (++ib == Cfg::kBStages) { ib = 0; phb ^= 1; }
+            b_ready = ptx::mbar_try_wait(&bfull_bar[ib], phb);
+          }
+          if (++ia == Cfg::kAStages) { ia = 0; pha ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    epilogue_warps<BN, NL, false, 0, false, true>(p, aux, s_scale, s_shift, tfull_bar, tempty_bar, stg_bar, tmem_base, warp, lane);
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
+  }
+}
 
 // ====================================================================================================
 // Split-K finisher: out = epilogue( sum_s partial[s] ).  One thread = one pixel x 8 channels.

@@ -96,6 +96,7 @@ struct PlanLayer {
   int bn = 64;
   int grid = 1;
   bool patch = false;     // conv_patch_kernel (halo patch per chunk) instead of conv_umma_kernel (one box per tap)
+  bool pair = false;      // conv_pair_kernel (cta_group::2)
   int cluster = 1;        // CTAs per cluster sharing B stages by TMA multicast (patch mode only)
   bool split = false;     // split-K: conv kernel writes fp32 partials, splitk_reduce_kernel finishes
   ReduceParams red;
@@ -441,6 +442,7 @@ struct Geo {
   int k_items;                 // K-loop length: K blocks (v1) or (source, chunk) items (patch)
   int n_split, split_len;
   size_t partial_bytes;
+  bool pair;                   // conv_pair_kernel: cta_group::2 UMMA over a 2-CTA cluster (wide layers)
 };
 
 Geo layer_geo(const lspg_ctx* h, const Layer& L, int B, int H, int W) {
@@ -460,11 +462,21 @@ Geo layer_geo(const lspg_ctx* h, const Layer& L, int B, int H, int W) {
   g.k_items = g.patch ? chunks : chunks * L.n_taps;
   if (L.kind == K_TAIL) g.bn = 16;
   else g.bn = (L.cout_pad % 128 == 0 && g.m_tiles * (L.cout_pad / 128) * L.n_phases >= h->num_sms_or_default()) ? 128 : 64;
+  // CTA-pair kernel for the wide layers: N tile 256 (or 128), two neighbouring M tiles per cluster
+  static const bool no_pair = getenv("LSPG_NO_PAIR") != nullptr;
+  g.pair = false;
+  if (!no_pair && g.patch && (L.kind == K_S1 || L.kind == K_UP) && L.cout_pad % 128 == 0 && g.m_tiles % 2 == 0) {
+    const int sms = h->num_sms_or_default();
+    int bnp = 0;
+    if (L.cout_pad % 256 == 0 && g.m_tiles * (L.cout_pad / 256) * L.n_phases >= sms) bnp = 256;
+    else if (g.m_tiles * (L.cout_pad / 128) * L.n_phases >= sms) bnp = 128;
+    if (bnp) { g.pair = true; g.bn = bnp; }
+  }
   g.n_tiles = L.cout_pad / g.bn;
   g.tiles_per_split = g.m_tiles * g.n_tiles * L.n_phases;
   g.n_split = 1; g.split_len = g.k_items; g.partial_bytes = 0;
   const int sms = h->num_sms_or_default();
-  if (!no_split && L.kind != K_TAIL && g.tiles_per_split * 2 <= sms) {
+  if (!no_split && !g.pair && L.kind != K_TAIL && g.tiles_per_split * 2 <= sms) {
     const int min_len = g.patch ? 1 : 4;                       // at least 4 K blocks (v1) / 1 chunk of all taps per split
     int want = (sms + g.tiles_per_split - 1) / g.tiles_per_split;
     int max_split = g.k_items / min_len;
@@ -570,7 +582,7 @@ int patch_tps(int bn, int NL, bool tail) {   // must mirror PatchCfg::kTPS
   return NL == 1 ? 3 : 2;
 }
 
-uint32_t make_idesc(int bn) {
+uint32_t make_idesc(int bn, int m = kTileM) {
   // cute::UMMA::InstrDescriptor bit layout: c_format[4,6)=1 (F32), a_format[7,10)=1 (BF16), b_format[10,13)=1,
   // a/b major [15],[16] = 0 (K-major), n_dim[17,23) = N>>3, m_dim[24,29) = M>>4
   uint32_t d = 0;
@@ -578,7 +590,7 @@ uint32_t make_idesc(int bn) {
   d |= 1u << 7;
   d |= 1u << 10;
   d |= static_cast<uint32_t>(bn >> 3) << 17;
-  d |= static_cast<uint32_t>(kTileM >> 4) << 24;
+  d |= static_cast<uint32_t>(m >> 4) << 24;
   return d;
 }
 
@@ -655,8 +667,8 @@ int build_plan(lspg_ctx* h, Plan* P, int B, int H, int W, int mode, void* worksp
     p.chunks[0] = L.cin[0] / 64; p.chunks[1] = L.n_src == 2 ? L.cin[1] / 64 : 0;
     p.relu = L.relu; p.has_res = L.res >= 0 ? 1 : 0;
     p.batch = B; p.hs = Hs; p.ws = Ws;
-    p.idesc = make_idesc(pl.bn);
-    p.idesc2 = make_idesc(2 * pl.bn);
+    p.idesc = g.pair ? make_idesc(pl.bn, 256) : make_idesc(pl.bn);
+    p.idesc2 = make_idesc(2 * pl.bn > 256 ? 256 : 2 * pl.bn);
     p.scale = L.d_scale; p.shift = L.d_shift; p.out_f32 = nullptr;
     memcpy(p.tap_map, L.tap_map, sizeof(p.tap_map));
     memcpy(p.tap_dx, L.tap_dx, sizeof(p.tap_dx));
@@ -680,8 +692,9 @@ int build_plan(lspg_ctx* h, Plan* P, int B, int H, int W, int mode, void* worksp
     for (int q = used; q < 4; ++q) p.a[q] = p.a[0];
     if (pl.patch) {
       static const bool no_cluster = getenv("LSPG_NO_CLUSTER") != nullptr;
-      pl.cluster = (!no_cluster && g.n_split == 1 && g.m_tiles % 2 == 0 && g.tiles_per_split >= h->num_sms) ? 2 : 1;
-      if (pl.cluster == 1 && NL == 1) rc = make_weight_map_taps(h, &p.w, L, pl.bn, patch_tps(pl.bn, NL, L.kind == K_TAIL));
+      pl.pair = g.pair;
+      pl.cluster = (g.pair || (!no_cluster && g.n_split == 1 && g.m_tiles % 2 == 0 && g.tiles_per_split >= h->num_sms)) ? 2 : 1;
+      if (pl.cluster == 1 && NL == 1 && !pl.pair) rc = make_weight_map_taps(h, &p.w, L, pl.bn, patch_tps(pl.bn, NL, L.kind == K_TAIL));
       else rc = make_weight_map_taps(h, &p.w, L, pl.bn / pl.cluster, 1);      // per-tap boxes (row slice per CTA when multicasting)
       if (rc) return rc;
     } else {
@@ -807,7 +820,23 @@ int launch_patch_cl(const ConvParams& p, int grid, int cluster, cudaStream_t st)
   return cluster == 2 ? launch_patch<BN, NL, TAIL, 2>(p, grid, st) : launch_patch<BN, NL, TAIL, 1>(p, grid, st);
 }
 
+template <int BN, int NL>
+int launch_pair(const ConvParams& p, int grid, cudaStream_t st) {
+  using Cfg = PairCfg<BN, NL>;
+  static bool configured = false;
+  if (!configured) {
+    CUDA_TRY(cudaFuncSetAttribute(conv_pair_kernel<BN, NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  CUDA_TRY(launch_pdl_cluster(conv_pair_kernel<BN, NL>, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, st, 2, p));
+  return LSPG_OK;
+}
+
 int launch_layer(const PlanLayer& pl, int kind, int NL, cudaStream_t st) {
+  if (pl.pair) {
+    if (pl.bn == 256) return NL == 1 ? launch_pair<256, 1>(pl.prm, pl.grid, st) : launch_pair<256, 2>(pl.prm, pl.grid, st);
+    return NL == 1 ? launch_pair<128, 1>(pl.prm, pl.grid, st) : launch_pair<128, 2>(pl.prm, pl.grid, st);
+  }
   if (pl.patch) {
     const int c = pl.cluster;
     if (kind == K_TAIL) return NL == 1 ? launch_patch_cl<16, 1, true>(pl.prm, pl.grid, c, st) : launch_patch_cl<16, 2, true>(pl.prm, pl.grid, c, st);
