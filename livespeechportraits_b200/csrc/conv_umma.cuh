@@ -32,7 +32,8 @@ constexpr int kTileM = 128;                 // output pixels per tile (UMMA M)
 constexpr int kChunk = 64;                  // channels per K block = 128 bytes of bf16 = one swizzle row
 constexpr int kATile = kTileM * 128;        // bytes of one A (or staging) tile
 constexpr int kMaxTaps = 9;
-constexpr int kThreads = 192;
+constexpr int kThreads = 192;            // 2 role warps + 4 epilogue warps
+constexpr int kThreadsWide = 320;        // 2 role warps + 8 epilogue warps (patch / pair kernels, non-tail)
 constexpr int kEpiThreads = 128;
 constexpr int kSmemBudget = 227 * 1024;
 
@@ -75,6 +76,7 @@ struct alignas(64) ConvParams {
   // partial[tile_index][128][BN]; splitk_reduce_kernel sums the splits and applies the epilogue.
   int32_t n_split, split_len, tiles_per_split;
   float* partial;
+  int32_t b_resident;            // pair kernel: every weight tile of the layer fits the B ring -> load once per CTA, no streaming
   int* split_counter;            // [tiles_per_split] arrival counters (zero between forwards); null = two-pass (finisher kernel)
   unsigned long long* trace;     // debug: per-CTA clock64 stamps (null in production), see kTraceSlots
   int32_t tap_rotate;            // patch mode: tile (x,y) dependent rotation of the tap order, so that concurrently
@@ -160,110 +162,119 @@ struct StgCfg {
 // STACK (parity mode of the patch kernel): the accumulator of a tile is 2*BN columns wide - columns [0,BN) hold
 // A_hi*B_hi + A_lo*B_hi, columns [BN,2BN) hold A_hi*B_lo (one N=2BN MMA over the stacked [B_hi;B_lo] tile) - and the
 // epilogue adds the two halves.
-template <int BN, int NL, bool TAIL, int NSTG, bool STACK, bool PAIR = false>
-__device__ __forceinline__ void epilogue_warps(const ConvParams& p, uint8_t* stg_base, float* s_scale0, float* /*unused*/,
+// EW = number of epilogue warps (4 or 8).  A warp may read TMEM lane quarter (warp % 4); with EW = 8 two warps share a
+// quarter and split the columns in interleaved 32-column pieces, which doubles the loads/stores in flight and the issue
+// slots of the epilogue (the 64-channel layers were epilogue-bound with 4 warps: 6.2k cycles vs 3.5k of MMAs per tile).
+template <int BN, int NL, bool TAIL, int NSTG, bool STACK, bool PAIR = false, int EW = 4>
+__device__ __forceinline__ void epilogue_warps(const ConvParams& p, uint8_t* /*stg_base*/, float* s_scale0, float* /*unused*/,
                                                uint64_t* tfull_bar, uint64_t* tempty_bar, uint64_t* stg_bar,
                                                uint32_t tmem_base, int warp, int lane) {
+  static_assert(EW == 4 || EW == 8, "4 or 8 epilogue warps");
+  static_assert(!(TAIL && EW != 4), "the tail epilogue uses 4 warps");
+  constexpr int kEpi = EW * 32;
+  constexpr int kGroups = EW / 4;
   int* fix_flag = reinterpret_cast<int*>(stg_bar + 2) + 1;   // smem word right after the TMEM-address slot
-  using Cfg = StgCfg<NSTG>;
-    // ===================================================================== epilogue (warps 2..5)
-    ptx::pdl_wait();   // residual reads, output / split-K partial writes must not overtake the previous kernel
-    const int q = warp & 3;                     // TMEM lane quarter this warp may read
-    const int row = q * 32 + lane;              // tile row = pixel index inside the tile
-    const int etid = threadIdx.x - 64;          // 0..127
-    const bool leader = (etid == 0);
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    uint32_t g = 0;                             // running staging-chunk counter (selects buffer + parity)
+  ptx::pdl_wait();   // residual reads, output / split-K partial writes must not overtake the previous kernel
+  const int q = warp & 3;                     // TMEM lane quarter this warp may read
+  const int grp = (warp - 2) >> 2;            // which interleaved share of the 32-column pieces this warp takes
+  const int row = q * 32 + lane;              // tile row = pixel index inside the tile
+  const int etid = threadIdx.x - 64;          // 0..kEpi-1
+  const bool leader = (etid == 0);
+  int acc = 0;
+  uint32_t acc_phase = 0;
+  auto release_tmem = [&]() {
+    ptx::tc_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+      if constexpr (PAIR) ptx::mbar_arrive_cluster(&tempty_bar[acc], 0);
+      else ptx::mbar_arrive(&tempty_bar[acc]);
+    }
+  };
 
-    constexpr int kChunksPerTile = TAIL ? 1 : BN / kChunk;
-    int lt = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++lt) {
-      const TileCoord tc = decode_tile(p, t);
-      if (leader) trace_stamp(p, 4 + 8 * lt + 3);
-      // folded BatchNorm parameters of this tile's channel range, double buffered by accumulator index: a warp that
-      // is already on the next tile must not overwrite values a slower warp still reads (no barrier after the math)
-      float* s_scale = s_scale0 + acc * 2 * BN;
-      float* s_shift = s_scale + BN;
-      for (int i = etid; i < BN; i += kEpiThreads) {
-        s_scale[i] = p.scale[tc.nt * BN + i];
-        s_shift[i] = p.shift[tc.nt * BN + i];
-      }
-      const bool split_mode = !TAIL && p.n_split > 1;
-      bool fixup = false;
-      ptx::named_bar_sync(1, kEpiThreads);
+  int lt = 0;
+  for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++lt) {
+    const TileCoord tc = decode_tile(p, t);
+    if (leader) trace_stamp(p, 4 + 8 * lt + 3);
+    // folded BatchNorm parameters of this tile's channel range, double buffered by accumulator index: a warp that
+    // is already on the next tile must not overwrite values a slower warp still reads (no barrier after the math)
+    float* s_scale = s_scale0 + acc * 2 * BN;
+    float* s_shift = s_scale + BN;
+    for (int i = etid; i < BN; i += kEpi) {
+      s_scale[i] = p.scale[tc.nt * BN + i];
+      s_shift[i] = p.shift[tc.nt * BN + i];
+    }
+    const bool split_mode = !TAIL && p.n_split > 1;
+    bool fixup = false;
+    ptx::named_bar_sync(1, kEpi);
 
-      ptx::mbar_wait(&tfull_bar[acc], acc_phase);
-      ptx::tc_fence_after();
-      if (leader) trace_stamp(p, 4 + 8 * lt + 4);
-      constexpr int kAccCols = STACK ? 2 * BN : BN;
-      const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccCols;
+    ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+    ptx::tc_fence_after();
+    if (leader) trace_stamp(p, 4 + 8 * lt + 4);
+    constexpr int kAccCols = STACK ? 2 * BN : BN;
+    const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccCols;
 
-      if constexpr (TAIL) {
-        // ---- tail: 16 columns = 4 phases x 3 channels (+4 pad); tanh; fp32 NCHW scatter
-        uint32_t v[16];
-        ptx::tmem_ld_32x16(t_acc, v);
-        if constexpr (STACK) {
-          uint32_t v2[16];
-          ptx::tmem_ld_32x16(t_acc + BN, v2);
-          ptx::tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
-        }
+    const int tw_ = row & ((1 << p.tw_log2) - 1);
+    const int th_ = (row >> p.tw_log2) & ((1 << p.th_log2) - 1);
+    const int nb_ = row >> (p.tw_log2 + p.th_log2);
+    const int pn = tc.n0 + nb_, py_ = tc.y0 + th_, px_ = tc.x0 + tw_;
+    const bool pix_ok = pn < p.batch && py_ < p.hs && px_ < p.ws;
+
+    if constexpr (TAIL) {
+      // ---- tail: 16 columns = 4 phases x 3 channels (+4 pad); tanh; fp32 NCHW scatter or fused tensor2im
+      uint32_t v[16];
+      ptx::tmem_ld_32x16(t_acc, v);
+      if constexpr (STACK) {
+        uint32_t v2[16];
+        ptx::tmem_ld_32x16(t_acc + BN, v2);
         ptx::tmem_ld_wait();
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) { if constexpr (PAIR) ptx::mbar_arrive_cluster(&tempty_bar[acc], 0); else ptx::mbar_arrive(&tempty_bar[acc]); }
-        const uint32_t* v_ = v;
-        const int tw = row & ((1 << p.tw_log2) - 1);
-        const int th = (row >> p.tw_log2) & ((1 << p.th_log2) - 1);
-        const int nb = row >> (p.tw_log2 + p.th_log2);
-        const int n = tc.n0 + nb, y = tc.y0 + th, x = tc.x0 + tw;
-        if (n < p.batch && y < p.hs && x < p.ws && p.out_u8 != nullptr) {
-          // fused util/util.py:tensor2im (reference lines 33-42): (x + 1) / 2 * 255 in fp32, clip to [0,255], truncate to
-          // uint8, CHW -> HWC.  This thread owns output pixels (2y+py, 2x+px): per py, 2 pixels x 3 channels = 6 bytes.
-          const int oh = 2 * p.hs, ow = 2 * p.ws;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
+      }
+      ptx::tmem_ld_wait();
+      release_tmem();
+      const int oh = 2 * p.hs, ow = 2 * p.ws;
+      if (pix_ok && p.out_u8 != nullptr) {
+        // fused util/util.py:tensor2im (reference lines 33-42): (x + 1) / 2 * 255 in fp32, clip to [0,255], truncate to
+        // uint8, CHW -> HWC.  This thread owns output pixels (2y+py, 2x+px): per py, 2 pixels x 3 channels = 6 bytes.
+#pragma unroll
+        for (int py = 0; py < 2; ++py) {
+          uint8_t b[6];
+#pragma unroll
+          for (int px = 0; px < 2; ++px)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              const int col = (py * 2 + px) * 3 + c;
+              const float vf = tanhf(__uint_as_float(v[col]) * s_scale[col] + s_shift[col]);
+              float u = __fmul_rn(__fmul_rn(__fadd_rn(vf, 1.0f), 0.5f), 255.0f);
+              u = fminf(fmaxf(u, 0.0f), 255.0f);
+              b[px * 3 + c] = static_cast<uint8_t>(static_cast<int>(u));
+            }
+          uint8_t* dst = p.out_u8 + ((static_cast<size_t>(pn) * oh + (2 * py_ + py)) * ow + 2 * px_) * 3;
+          uint16_t* d16 = reinterpret_cast<uint16_t*>(dst);          // 6-byte aligned: 2x * 3 is even
+          d16[0] = static_cast<uint16_t>(b[0] | (b[1] << 8));
+          d16[1] = static_cast<uint16_t>(b[2] | (b[3] << 8));
+          d16[2] = static_cast<uint16_t>(b[4] | (b[5] << 8));
+        }
+      } else if (pix_ok) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
 #pragma unroll
           for (int py = 0; py < 2; ++py) {
-            uint8_t b[6];
-#pragma unroll
-            for (int px = 0; px < 2; ++px)
-#pragma unroll
-              for (int c = 0; c < 3; ++c) {
-                const int col = (py * 2 + px) * 3 + c;
-                const float v = tanhf(__uint_as_float(v_[col]) * s_scale[col] + s_shift[col]);
-                float u = __fmul_rn(__fmul_rn(__fadd_rn(v, 1.0f), 0.5f), 255.0f);
-                u = fminf(fmaxf(u, 0.0f), 255.0f);
-                b[px * 3 + c] = static_cast<uint8_t>(static_cast<int>(u));
-              }
-            uint8_t* dst = p.out_u8 + ((static_cast<size_t>(n) * oh + (2 * y + py)) * ow + 2 * x) * 3;
-            uint16_t* d16 = reinterpret_cast<uint16_t*>(dst);          // 6-byte aligned: 2x * 3 is even
-            d16[0] = static_cast<uint16_t>(b[0] | (b[1] << 8));
-            d16[1] = static_cast<uint16_t>(b[2] | (b[3] << 8));
-            d16[2] = static_cast<uint16_t>(b[4] | (b[5] << 8));
-          }
-        } else if (n < p.batch && y < p.hs && x < p.ws) {
-          const int oh = 2 * p.hs, ow = 2 * p.ws;
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-#pragma unroll
-            for (int py = 0; py < 2; ++py) {
-              float2 o;
-              o.x = tanhf(__uint_as_float(v[(py * 2 + 0) * 3 + c]) * s_scale[(py * 2 + 0) * 3 + c] +
-                          s_shift[(py * 2 + 0) * 3 + c]);
-              o.y = tanhf(__uint_as_float(v[(py * 2 + 1) * 3 + c]) * s_scale[(py * 2 + 1) * 3 + c] +
-                          s_shift[(py * 2 + 1) * 3 + c]);
-              float* dst = p.out_f32 + ((static_cast<size_t>(n) * 3 + c) * oh + (2 * y + py)) * ow + 2 * x;
-              *reinterpret_cast<float2*>(dst) = o;
-            }
+            float2 o;
+            o.x = tanhf(__uint_as_float(v[(py * 2 + 0) * 3 + c]) * s_scale[(py * 2 + 0) * 3 + c] + s_shift[(py * 2 + 0) * 3 + c]);
+            o.y = tanhf(__uint_as_float(v[(py * 2 + 1) * 3 + c]) * s_scale[(py * 2 + 1) * 3 + c] + s_shift[(py * 2 + 1) * 3 + c]);
+            float* dst = p.out_f32 + ((static_cast<size_t>(pn) * 3 + c) * oh + (2 * py_ + py)) * ow + 2 * px_;
+            *reinterpret_cast<float2*>(dst) = o;
           }
         }
-      } else if constexpr (!TAIL) {
-       if (split_mode) {
+      }
+    } else {
+      constexpr int kPieces = BN / 32;             // 32-column pieces of the tile; this warp takes grp, grp+kGroups, ...
+      if (split_mode) {
         // ---- split-K partial: raw fp32 accumulator rows -> partial[t][row][BN]
         float* dst = p.partial + (static_cast<size_t>(t) * kTileM + row) * BN;
 #pragma unroll 1
-        for (int c32 = 0; c32 < BN / 32; ++c32) {
+        for (int c32 = grp; c32 < kPieces; c32 += kGroups) {
           uint32_t v[32];
           ptx::tmem_ld_32x32(t_acc + c32 * 32, v);
           if constexpr (STACK) {
@@ -274,20 +285,16 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, uint8_t* stg
             for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
           }
           ptx::tmem_ld_wait();
-          if (c32 == BN / 32 - 1) {
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) { if constexpr (PAIR) ptx::mbar_arrive_cluster(&tempty_bar[acc], 0); else ptx::mbar_arrive(&tempty_bar[acc]); }
-          }
+          if (c32 + kGroups >= kPieces) release_tmem();
 #pragma unroll
           for (int e = 0; e < 8; ++e)
             *reinterpret_cast<uint4*>(dst + c32 * 32 + e * 4) = make_uint4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
         }
         if (p.split_counter != nullptr) {
-          // In-kernel finish: the CTA that publishes the LAST partial of an output tile sums all of them (in split
-          // order, so the result does not depend on which CTA that is) and runs the regular epilogue below.
+          // In-kernel finish (opt-in, LSPG_SPLITK_FIXUP): the CTA that publishes the LAST partial of an output tile sums
+          // all of them (in split order, so the result does not depend on which CTA that is) and runs the epilogue below.
           __threadfence();
-          ptx::named_bar_sync(2, kEpiThreads);
+          ptx::named_bar_sync(2, kEpi);
           if (leader) {
             const int tile_id = t - tc.split * p.tiles_per_split;
             const int old = atomicAdd(p.split_counter + tile_id, 1);
@@ -295,60 +302,52 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, uint8_t* stg
             if (last) p.split_counter[tile_id] = 0;          // ready for the next forward
             *fix_flag = last;
           }
-          ptx::named_bar_sync(3, kEpiThreads);
+          ptx::named_bar_sync(3, kEpi);
           fixup = (*fix_flag != 0);
           __threadfence();
           if (fixup) {
-            // cooperative, coalesced reduction of the tile: thread i owns float4 i, i+128, ... ; splits are added in
-            // order 0,1,2,... (deterministic), four loads in flight per accumulator; the sum replaces split 0's partial
             float* base = p.partial + static_cast<size_t>(t - tc.split * p.tiles_per_split) * kTileM * BN;
             const size_t split_stride = static_cast<size_t>(p.tiles_per_split) * kTileM * BN;
-            auto ldcg = [](const float* q) {
+            auto ldcg = [](const float* qq) {
               float4 a;
-              asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(q));
+              asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(qq));
               return a;
             };
-            for (int k = etid; k < kTileM * BN / 4; k += kEpiThreads) {
-              float* q = base + static_cast<size_t>(k) * 4;
-              float4 acc4 = ldcg(q);
+            for (int k = etid; k < kTileM * BN / 4; k += kEpi) {
+              float* qq = base + static_cast<size_t>(k) * 4;
+              float4 acc4 = ldcg(qq);
               int sp = 1;
               for (; sp + 4 <= p.n_split; sp += 4) {
-                const float4 a0 = ldcg(q + (sp + 0) * split_stride), a1 = ldcg(q + (sp + 1) * split_stride);
-                const float4 a2 = ldcg(q + (sp + 2) * split_stride), a3 = ldcg(q + (sp + 3) * split_stride);
+                const float4 a0 = ldcg(qq + (sp + 0) * split_stride), a1 = ldcg(qq + (sp + 1) * split_stride);
+                const float4 a2 = ldcg(qq + (sp + 2) * split_stride), a3 = ldcg(qq + (sp + 3) * split_stride);
                 acc4.x += a0.x; acc4.y += a0.y; acc4.z += a0.z; acc4.w += a0.w;
                 acc4.x += a1.x; acc4.y += a1.y; acc4.z += a1.z; acc4.w += a1.w;
                 acc4.x += a2.x; acc4.y += a2.y; acc4.z += a2.z; acc4.w += a2.w;
                 acc4.x += a3.x; acc4.y += a3.y; acc4.z += a3.z; acc4.w += a3.w;
               }
               for (; sp < p.n_split; ++sp) {
-                const float4 a0 = ldcg(q + sp * split_stride);
+                const float4 a0 = ldcg(qq + sp * split_stride);
                 acc4.x += a0.x; acc4.y += a0.y; acc4.z += a0.z; acc4.w += a0.w;
               }
-              *reinterpret_cast<float4*>(q) = acc4;
+              *reinterpret_cast<float4*>(qq) = acc4;
             }
             __threadfence();
-            ptx::named_bar_sync(2, kEpiThreads);
+            ptx::named_bar_sync(2, kEpi);
           }
         }
-       }
-       if (!split_mode || fixup) {
+      }
+      if (!split_mode || fixup) {
         // ---- regular: scale/shift (+ residual) + ReLU, bf16 (hi, lo), written straight to the NHWC output.
-        // Each thread owns one pixel: it reads its residual row and writes its output row (64 channels = 128
-        // contiguous bytes per chunk and limb) with plain 16-byte global accesses.  No smem staging and no TMA
-        // store: a TMA store queues behind the producer's outstanding TMA loads in the SM's TMA pipe, and waiting
-        // for its smem read cost ~3 us per 64-channel chunk (measured), which made the epilogue - not the tensor
-        // pipe - the per-tile critical path.  Global stores are fire-and-forget.
-        const int tw_ = row & ((1 << p.tw_log2) - 1);
-        const int th_ = (row >> p.tw_log2) & ((1 << p.th_log2) - 1);
-        const int nb_ = row >> (p.tw_log2 + p.th_log2);
-        const int pn = tc.n0 + nb_, py_ = tc.y0 + th_, px_ = tc.x0 + tw_;
-        const bool pix_ok = pn < p.batch && py_ < p.hs && px_ < p.ws;
+        // Each thread owns one pixel row; per 32-column piece it reads its residual (64 B per limb) and writes its output
+        // with 256-bit (one 32-byte sector) global accesses.  No smem staging and no TMA store: a TMA store queues behind
+        // the producer's outstanding TMA loads in the SM's TMA pipe (measured ~3 us per chunk), and global stores are
+        // fire-and-forget.
         const int oh = p.out_up ? 2 * p.hs : p.hs, ow = p.out_up ? 2 * p.ws : p.ws;
         const int oy = p.out_up ? 2 * py_ + (tc.z >> 1) : py_, ox = p.out_up ? 2 * px_ + (tc.z & 1) : px_;
         __nv_bfloat16* out_row = p.out_ptr + ((static_cast<size_t>(pn) * oh + oy) * ow + ox) * p.out_channels + tc.nt * BN;
         const __nv_bfloat16* res_row = p.res_ptr + ((static_cast<size_t>(pn) * p.hs + py_) * p.ws + px_) * p.res_channels +
                                        tc.nt * BN;
-        if (p.has_res) {
+        if (p.has_res && grp == kGroups - 1) {
           // pull the residual rows of this CTA's NEXT tile towards L2 while this tile is being finished
           const int t2 = t + gridDim.x;
           if (t2 < p.total_tiles) {
@@ -359,70 +358,60 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, uint8_t* stg
 #pragma unroll
               for (int l = 0; l < NL; ++l)
 #pragma unroll
-                for (int c = 0; c < kChunksPerTile; ++c)
-                  asm volatile("prefetch.global.L2 [%0];" ::"l"(r2 + l * p.res_limb_stride + c * kChunk));
+                for (int c = 0; c < BN / 16; ++c)        // every 32-byte sector of the row (a prefetch moves one sector)
+                  asm volatile("prefetch.global.L2 [%0];" ::"l"(r2 + l * p.res_limb_stride + c * 16));
             }
           }
         }
-        for (int chunk = 0; chunk < kChunksPerTile; ++chunk) {
-          uint4 rs[NL][8];                                   // residual: 64 channels x NL limbs of this pixel
+#pragma unroll 1
+        for (int c32 = grp; c32 < kPieces; c32 += kGroups) {
+          uint4 rs[NL][4];                                   // residual: 32 channels x NL limbs of this pixel
           if (p.has_res) {
 #pragma unroll
             for (int l = 0; l < NL; ++l)
 #pragma unroll
-              for (int c32 = 0; c32 < 4; ++c32) {
+              for (int h2 = 0; h2 < 2; ++h2) {
                 if (pix_ok) {
-                  ptx::ldg256_nc(res_row + l * p.res_limb_stride + chunk * kChunk + c32 * 16, rs[l][2 * c32], rs[l][2 * c32 + 1]);
+                  ptx::ldg256_nc(res_row + l * p.res_limb_stride + c32 * 32 + h2 * 16, rs[l][2 * h2], rs[l][2 * h2 + 1]);
                 } else {
-                  rs[l][2 * c32] = make_uint4(0u, 0u, 0u, 0u);
-                  rs[l][2 * c32 + 1] = make_uint4(0u, 0u, 0u, 0u);
+                  rs[l][2 * h2] = make_uint4(0u, 0u, 0u, 0u);
+                  rs[l][2 * h2 + 1] = make_uint4(0u, 0u, 0u, 0u);
                 }
               }
           }
-          uint32_t vv[2][32];
+          uint32_t vv[32];
           if (fixup) {
             // the summed tile was written back to split 0's slot by the cooperative pass above
-            const float* src0 = p.partial + (static_cast<size_t>(t - tc.split * p.tiles_per_split) * kTileM + row) * BN + chunk * kChunk;
+            const float* src0 = p.partial + (static_cast<size_t>(t - tc.split * p.tiles_per_split) * kTileM + row) * BN + c32 * 32;
 #pragma unroll
-            for (int hf = 0; hf < 2; ++hf)
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                float4 a;
-                asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(src0 + hf * 32 + e * 4));
-                vv[hf][4 * e] = __float_as_uint(a.x);
-                vv[hf][4 * e + 1] = __float_as_uint(a.y);
-                vv[hf][4 * e + 2] = __float_as_uint(a.z);
-                vv[hf][4 * e + 3] = __float_as_uint(a.w);
-              }
+            for (int e = 0; e < 8; ++e) {
+              float4 a;
+              asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(src0 + e * 4));
+              vv[4 * e] = __float_as_uint(a.x);
+              vv[4 * e + 1] = __float_as_uint(a.y);
+              vv[4 * e + 2] = __float_as_uint(a.z);
+              vv[4 * e + 3] = __float_as_uint(a.w);
+            }
           } else {
-          ptx::tmem_ld_32x32(t_acc + chunk * kChunk, vv[0]);
-          ptx::tmem_ld_32x32(t_acc + chunk * kChunk + 32, vv[1]);
-          if constexpr (STACK) {
-#pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
+            ptx::tmem_ld_32x32(t_acc + c32 * 32, vv);
+            if constexpr (STACK) {
               uint32_t v2[32];
-              ptx::tmem_ld_32x32(t_acc + BN + chunk * kChunk + hf * 32, v2);
+              ptx::tmem_ld_32x32(t_acc + BN + c32 * 32, v2);
               ptx::tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 32; ++i) vv[hf][i] = __float_as_uint(__uint_as_float(vv[hf][i]) + __uint_as_float(v2[i]));
+              for (int i = 0; i < 32; ++i) vv[i] = __float_as_uint(__uint_as_float(vv[i]) + __uint_as_float(v2[i]));
             }
-          }
-          ptx::tmem_ld_wait();
-          if (chunk == kChunksPerTile - 1) {
-            // accumulator fully drained into registers: hand the TMEM buffer back to the MMA warp
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) { if constexpr (PAIR) ptx::mbar_arrive_cluster(&tempty_bar[acc], 0); else ptx::mbar_arrive(&tempty_bar[acc]); }
-          }
+            ptx::tmem_ld_wait();
+            if (c32 + kGroups >= kPieces) release_tmem();   // this warp's share of the accumulator is in registers
           }
           uint4 o_prev = make_uint4(0u, 0u, 0u, 0u), ol_prev = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-          for (int piece = 0; piece < 8; ++piece) {          // 16-byte pieces: 8 channels each
+          for (int piece = 0; piece < 4; ++piece) {          // 16-byte pieces: 8 channels each
             float y[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              const int ch = chunk * kChunk + piece * 8 + e;
-              y[e] = fmaf(__uint_as_float(vv[piece >> 2][(piece & 3) * 8 + e]), s_scale[ch], s_shift[ch]);
+              const int ch = c32 * 32 + piece * 8 + e;
+              y[e] = fmaf(__uint_as_float(vv[piece * 8 + e]), s_scale[ch], s_shift[ch]);
             }
             if (p.has_res) {
 #pragma unroll
@@ -455,8 +444,8 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, uint8_t* stg
             }
             if (piece & 1) {               // two 16-byte pieces = one 32-byte sector per store
               if (pix_ok) {
-                ptx::stg256(out_row + chunk * kChunk + (piece - 1) * 8, o_prev, o);
-                if (NL == 2) ptx::stg256(out_row + p.out_limb_stride + chunk * kChunk + (piece - 1) * 8, ol_prev, ol);
+                ptx::stg256(out_row + c32 * 32 + (piece - 1) * 8, o_prev, o);
+                if (NL == 2) ptx::stg256(out_row + p.out_limb_stride + c32 * 32 + (piece - 1) * 8, ol_prev, ol);
               }
             } else {
               o_prev = o;
@@ -464,11 +453,11 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, uint8_t* stg
             }
           }
         }
-       }
       }
-      if (leader) trace_stamp(p, 4 + 8 * lt + 5);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (leader) trace_stamp(p, 4 + 8 * lt + 5);
+    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+  }
 }
 
 template <int BN, int NL, bool TAIL>
@@ -665,8 +654,8 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_strided(uint32_t smem_addr, 
 // to both (cp.async.bulk.tensor ... .multicast::cluster), halving the L2->SM weight traffic that clock64 traces showed
 // to be the limiter (~30-36 B/clk/SM of weight tiles, every SM asking L2 for the same lines).  A stage is refilled
 // only after BOTH CTAs' MMAs released it (tcgen05.commit ... .multicast::cluster onto both bempty barriers).
-template <int BN, int NL, bool TAIL, int CL>
-__global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_constant__ ConvParams p) {
+template <int BN, int NL, bool TAIL, int CL, int EW>
+__global__ void __launch_bounds__(64 + EW * 32, 1) conv_patch_kernel(const __grid_constant__ ConvParams p) {
   using Cfg = PatchCfg<BN, NL, TAIL>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -700,7 +689,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
     for (int i = 0; i < Cfg::kBStages; ++i) { ptx::mbar_init(&bfull_bar[i], 1); ptx::mbar_init(&bempty_bar[i], CL); }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tfull_bar[i], 1);
-      ptx::mbar_init(&tempty_bar[i], 4);
+      ptx::mbar_init(&tempty_bar[i], EW);   // one arrive per epilogue warp
       ptx::mbar_init(&stg_bar[i], 1);
     }
     ptx::fence_mbar_init();
@@ -862,7 +851,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
-    epilogue_warps<BN, NL, TAIL, Cfg::kNumStg, (NL == 2)>(p, stg_base, s_scale, s_shift, tfull_bar, tempty_bar, stg_bar, tmem_base, warp, lane);
+    epilogue_warps<BN, NL, TAIL, Cfg::kNumStg, (NL == 2), false, EW>(p, stg_base, s_scale, s_shift, tfull_bar, tempty_bar, stg_bar, tmem_base, warp, lane);
   }
 
   ptx::tc_fence_before();
@@ -893,17 +882,17 @@ struct PairCfg {
   static constexpr int kAux = 5120;
   static constexpr int kAvail = kSmemBudget - 1024 - kAux - kAStages * kAStage;
   static constexpr int kBStagesRaw = kAvail / kBStage;
-  static constexpr int kBStages = kBStagesRaw > 12 ? 12 : kBStagesRaw;
+  static constexpr int kBStages = kBStagesRaw > 16 ? 16 : kBStagesRaw;
   static constexpr int kSmemBytes = 1024 + kAStages * kAStage + kBStages * kBStage + kAux;
   static constexpr int kTmemCols = 2 * BN;
-  static_assert(BN == 128 || BN == 256, "pair kernel: N tile 128 or 256");
+  static_assert(BN == 64 || BN == 128 || BN == 256, "pair kernel: N tile 64, 128 or 256");
   static_assert(kTmemCols <= 512, "TMEM has 512 columns");
   static_assert(kBStages >= 3, "B ring too shallow");
-  static_assert(4 * BN * 4 + (2 * 12 + 2 * 2 + 8) * 8 <= kAux, "aux region too small");
+  static_assert(4 * BN * 4 + (2 * 16 + 2 * 2 + 8) * 8 <= kAux, "aux region too small");
 };
 
-template <int BN, int NL>
-__global__ void __launch_bounds__(kThreads, 1) conv_pair_kernel(const __grid_constant__ ConvParams p) {
+template <int BN, int NL, int EW>
+__global__ void __launch_bounds__(64 + EW * 32, 1) conv_pair_kernel(const __grid_constant__ ConvParams p) {
   using Cfg = PairCfg<BN, NL>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -934,7 +923,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_pair_kernel(const __grid_con
     for (int i = 0; i < Cfg::kBStages; ++i) { ptx::mbar_init(&bfull_bar[i], 1); ptx::mbar_init(&bempty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tfull_bar[i], 1);
-      ptx::mbar_init(&tempty_bar[i], 8);       // 4 epilogue warps of each CTA of the pair
+      ptx::mbar_init(&tempty_bar[i], 2 * EW);  // the epilogue warps of both CTAs of the pair
       ptx::mbar_init(&stg_bar[i], 1);
     }
     ptx::fence_mbar_init();
@@ -978,12 +967,33 @@ __global__ void __launch_bounds__(kThreads, 1) conv_pair_kernel(const __grid_con
       if (++ia == Cfg::kAStages) { ia = 0; pha ^= 1; }
       if (++a_ci == kb_per_tap) { a_ci = 0; a_tile += gridDim.x; }
     };
+    if (p.b_resident) {
+      // all weight tiles of the layer (this CTA's half of each) are loaded once; one barrier covers them
+      if (blockIdx.x < p.total_tiles) {
+        const TileCoord tc = decode_tile(p, blockIdx.x);      // nt and phase are the same for every tile of a resident layer
+        if (ptx::elect_one()) {
+          const int n_items = kb_per_tap * p.n_taps;
+          if (leader_cta) ptx::mbar_expect_tx(&bfull_bar[0], 2 * n_items * Cfg::kBStage);
+          for (int ci = 0; ci < kb_per_tap; ++ci)
+            for (int tap = 0; tap < p.n_taps; ++tap)
+#pragma unroll
+              for (int l = 0; l < NL; ++l)
+                ptx::tma_load_4d_pair(&p.w, &bfull_bar[0], b_ring + (ci * p.n_taps + tap) * Cfg::kBStage + l * Cfg::kBHalf,
+                                      ci * kChunk, tc.nt * BN + static_cast<int>(crank) * (BN / 2), tap, l * p.n_phases + tc.z);
+        }
+        __syncwarp();
+      }
+    }
     issue_a();
     const int a_after = (p.n_taps > 2) ? 2 : p.n_taps - 1;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
       const TileCoord tc = decode_tile(p, t);
       for (int ci = 0; ci < kb_per_tap; ++ci) {
         for (int tap = 0; tap < p.n_taps; ++tap) {
+          if (p.b_resident) {
+            if (tap == a_after) issue_a();
+            continue;
+          }
           ptx::mbar_wait(&bempty_bar[ib], phb ^ 1);
           if (ptx::elect_one()) {
             uint8_t* st = b_ring + ib * Cfg::kBStage;
@@ -1008,6 +1018,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_pair_kernel(const __grid_con
       uint32_t acc_phase = 0;
       const uint32_t sbo = static_cast<uint32_t>(p.patch_w) * 128u;
       bool b_ready = false;
+      const bool resident = p.b_resident != 0;
+      if (resident && blockIdx.x < p.total_tiles) { ptx::mbar_wait(&bfull_bar[0], 0); b_ready = true; }
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         int z, split;
         decode_tile_zs(p, t, z, split);
@@ -1021,7 +1033,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_pair_kernel(const __grid_con
             if (!b_ready) ptx::mbar_wait(&bfull_bar[ib], phb);
             ptx::tc_fence_after();
             if (ptx::elect_one()) {
-              const uint32_t b0 = ptx::smem_u32(b_ring + ib * Cfg::kBStage);
+              const uint32_t b0 = ptx::smem_u32(b_ring + (resident ? ci * p.n_taps + tap : ib) * Cfg::kBStage);
               const uint32_t a_hi_addr = a0 + static_cast<uint32_t>(p.tap_row[z][tap]) * 128u;
               const uint64_t a_hi = umma_desc_sw128_strided(a_hi_addr, sbo, false);
               const uint64_t b_hi = ptx::umma_desc_sw128(b0);
@@ -1036,15 +1048,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_pair_kernel(const __grid_con
                   ptx::umma_f16_pair(d_tmem, a_lo + 2 * k, b_hi + 2 * k, p.idesc, 1u);
                 }
               }
-              ptx::umma_commit_pair(&bempty_bar[ib], kMask);
+              if (!resident) ptx::umma_commit_pair(&bempty_bar[ib], kMask);
               if (tap == p.n_taps - 1) {
                 ptx::umma_commit_pair(&aempty_bar[ia], kMask);
                 if (ci == kb_per_tap - 1) ptx::umma_commit_pair(&tfull_bar[acc], kMask);
               }
             }
             __syncwarp();
-            if (++ib == Cfg::kBStages) { ib = 0; phb ^= 1; }
-            b_ready = ptx::mbar_try_wait(&bfull_bar[ib], phb);
+            if (!resident) {
+              if (++ib == Cfg::kBStages) { ib = 0; phb ^= 1; }
+              b_ready = ptx::mbar_try_wait(&bfull_bar[ib], phb);
+            }
           }
           if (++ia == Cfg::kAStages) { ia = 0; pha ^= 1; }
         }
@@ -1052,7 +1066,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_pair_kernel(const __grid_con
       }
     }
   } else {
-    epilogue_warps<BN, NL, false, 0, false, true>(p, aux, s_scale, s_shift, tfull_bar, tempty_bar, stg_bar, tmem_base, warp, lane);
+    epilogue_warps<BN, NL, false, 0, false, true, EW>(p, aux, s_scale, s_shift, tfull_bar, tempty_bar, stg_bar, tmem_base, warp, lane);
   }
 
   ptx::tc_fence_before();

@@ -465,11 +465,15 @@ Geo layer_geo(const lspg_ctx* h, const Layer& L, int B, int H, int W) {
   // CTA-pair kernel for the wide layers: N tile 256 (or 128), two neighbouring M tiles per cluster
   static const bool no_pair = getenv("LSPG_NO_PAIR") != nullptr;
   g.pair = false;
-  if (!no_pair && g.patch && (L.kind == K_S1 || L.kind == K_UP) && L.cout_pad % 128 == 0 && g.m_tiles % 2 == 0) {
+  if (!no_pair && g.patch && (L.kind == K_S1 || L.kind == K_UP) && L.cout_pad % 64 == 0 && g.m_tiles % 2 == 0) {
     const int sms = h->num_sms_or_default();
     int bnp = 0;
+    // a pair tile runs the tensor pipe at full rate while the N=64 single-CTA tile is shared-memory bound at ~60 %,
+    // so the pair kernel already wins when its tiles fill about two thirds of the SMs
+    const int enough = sms * 2 / 3;
     if (L.cout_pad % 256 == 0 && g.m_tiles * (L.cout_pad / 256) * L.n_phases >= sms) bnp = 256;
-    else if (g.m_tiles * (L.cout_pad / 128) * L.n_phases >= sms) bnp = 128;
+    else if (L.cout_pad % 128 == 0 && g.m_tiles * (L.cout_pad / 128) * L.n_phases >= enough) bnp = 128;
+    else if (L.cout_pad == 64 && g.m_tiles * L.n_phases >= enough) bnp = 64;
     if (bnp) { g.pair = true; g.bn = bnp; }
   }
   g.n_tiles = L.cout_pad / g.bn;
@@ -655,6 +659,13 @@ int build_plan(lspg_ctx* h, Plan* P, int B, int H, int W, int mode, void* worksp
     p.tiles_per_split = g.tiles_per_split;
     p.n_split = g.n_split; p.split_len = g.split_len;
     p.total_tiles = g.tiles_per_split * g.n_split;
+    if (g.pair) {
+      static const bool no_resident = getenv("LSPG_NO_RESIDENT") != nullptr;
+      const int n_items = g.k_items * L.n_taps;                           // weight tiles per output tile
+      const int stage = NL * (g.bn / 2) * 128;
+      const int cap = std::min(16, (kSmemBudget - 1024 - 5120 - 2 * NL * kPatchStride) / stage);
+      p.b_resident = (!no_resident && L.n_phases == 1 && g.n_tiles == 1 && n_items <= cap) ? 1 : 0;
+    }
     p.partial = reinterpret_cast<float*>(ws_scratch + kCounterBytes);
     // Measured on B200: letting the last-arriving CTA sum the partials in-kernel (LSPG_SPLITK_FIXUP=1) is slower than a
     // separate finisher kernel (B=1: 2.19 vs 1.44 ms per frame) - one CTA's 128 threads reduce a tile far more slowly
@@ -802,39 +813,52 @@ int launch_conv(const ConvParams& p, int grid, cudaStream_t st) {
   return LSPG_OK;
 }
 
-template <int BN, int NL, bool TAIL, int CL>
+int epi_warps() {     // 4 or 8 epilogue warps for the non-tail patch / pair kernels (A/B switch: LSPG_EPI_WARPS)
+  static const int v = [] { const char* e = getenv("LSPG_EPI_WARPS"); return (e && atoi(e) == 4) ? 4 : 8; }();
+  return v;
+}
+
+template <int BN, int NL, bool TAIL, int CL, int EW>
 int launch_patch(const ConvParams& p, int grid, cudaStream_t st) {
   using Cfg = PatchCfg<BN, NL, TAIL>;
   static bool configured = false;
   if (!configured) {
-    CUDA_TRY(cudaFuncSetAttribute(conv_patch_kernel<BN, NL, TAIL, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CUDA_TRY(cudaFuncSetAttribute(conv_patch_kernel<BN, NL, TAIL, CL, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   Cfg::kSmemBytes));
     configured = true;
   }
-  CUDA_TRY(launch_pdl_cluster(conv_patch_kernel<BN, NL, TAIL, CL>, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, st, CL, p));
+  CUDA_TRY(launch_pdl_cluster(conv_patch_kernel<BN, NL, TAIL, CL, EW>, dim3(grid), dim3(64 + EW * 32), Cfg::kSmemBytes, st, CL, p));
   return LSPG_OK;
 }
 
 template <int BN, int NL, bool TAIL>
 int launch_patch_cl(const ConvParams& p, int grid, int cluster, cudaStream_t st) {
-  return cluster == 2 ? launch_patch<BN, NL, TAIL, 2>(p, grid, st) : launch_patch<BN, NL, TAIL, 1>(p, grid, st);
+  if (TAIL || epi_warps() == 4)
+    return cluster == 2 ? launch_patch<BN, NL, TAIL, 2, 4>(p, grid, st) : launch_patch<BN, NL, TAIL, 1, 4>(p, grid, st);
+  return cluster == 2 ? launch_patch<BN, NL, TAIL, 2, (TAIL ? 4 : 8)>(p, grid, st) : launch_patch<BN, NL, TAIL, 1, (TAIL ? 4 : 8)>(p, grid, st);
+}
+
+template <int BN, int NL, int EW>
+int launch_pair_ew(const ConvParams& p, int grid, cudaStream_t st) {
+  using Cfg = PairCfg<BN, NL>;
+  static bool configured = false;
+  if (!configured) {
+    CUDA_TRY(cudaFuncSetAttribute(conv_pair_kernel<BN, NL, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  CUDA_TRY(launch_pdl_cluster(conv_pair_kernel<BN, NL, EW>, dim3(grid), dim3(64 + EW * 32), Cfg::kSmemBytes, st, 2, p));
+  return LSPG_OK;
 }
 
 template <int BN, int NL>
 int launch_pair(const ConvParams& p, int grid, cudaStream_t st) {
-  using Cfg = PairCfg<BN, NL>;
-  static bool configured = false;
-  if (!configured) {
-    CUDA_TRY(cudaFuncSetAttribute(conv_pair_kernel<BN, NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    configured = true;
-  }
-  CUDA_TRY(launch_pdl_cluster(conv_pair_kernel<BN, NL>, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, st, 2, p));
-  return LSPG_OK;
+  return epi_warps() == 4 ? launch_pair_ew<BN, NL, 4>(p, grid, st) : launch_pair_ew<BN, NL, 8>(p, grid, st);
 }
 
 int launch_layer(const PlanLayer& pl, int kind, int NL, cudaStream_t st) {
   if (pl.pair) {
     if (pl.bn == 256) return NL == 1 ? launch_pair<256, 1>(pl.prm, pl.grid, st) : launch_pair<256, 2>(pl.prm, pl.grid, st);
+    if (pl.bn == 64) return NL == 1 ? launch_pair<64, 1>(pl.prm, pl.grid, st) : launch_pair<64, 2>(pl.prm, pl.grid, st);
     return NL == 1 ? launch_pair<128, 1>(pl.prm, pl.grid, st) : launch_pair<128, 2>(pl.prm, pl.grid, st);
   }
   if (pl.patch) {
