@@ -25,6 +25,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.dont_write_bytecode = True
 
+import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 METRIC = "512x512 frames/sec (Feature2Face_G large / May.yaml)"
@@ -362,6 +363,29 @@ def main():
         dt8 = time.perf_counter() - t8
         extras["e2e_uint8_images"] = {"value": n_clip / dt8, "unit": "frames/s", "d2h_bytes_per_step": B * H * W * 3,
                                       "api": "ClipRenderer(uint8=True): lspg_forward_image (tensor2im fused, util/util.py:19-42)"}
+        # N2: landmark tracks in, uint8 images out - the maps are drawn on the GPU (lspg_draw_feature_maps), so
+        # 728 B per frame cross PCIe instead of 1 MB; the host-side cost this removes (88 cv2.line calls per frame,
+        # datasets/face_dataset.py:312-323) is timed next to it on one host thread, as the reference runs it
+        from oracle import raster_oracle as RO
+        lm_np, sh_np = RO.make_landmarks(n_clip, (W, H), seed=3)
+        lm_host, sh_host = torch.from_numpy(lm_np).pin_memory(), torch.from_numpy(sh_np).pin_memory()
+        clip8.render_clip_from_landmarks(lm_host[: B * 2], sh_host[: B * 2], cand, img_host[: B * 2], (W, H))
+        torch.cuda.synchronize()
+        tl = time.perf_counter()
+        clip8.render_clip_from_landmarks(lm_host, sh_host, cand, img_host, (W, H))
+        torch.cuda.synchronize()
+        dtl = time.perf_counter() - tl
+        ms_r = timed(lambda: net.draw_feature_maps(lm_host[:B].cuda(), sh_host[:B].cuda(), (W, H)), 20)
+        chk = net.draw_feature_maps(lm_host[:2].cuda(), sh_host[:2].cuda(), (W, H)).cpu().numpy()
+        exact = all(np.array_equal(chk[i, 0] * 255, RO.draw_feature_map_cv2(lm_np[i], (W, H), sh_np[i])) for i in range(2))
+        t_cv = time.perf_counter()
+        for i in range(32):
+            RO.draw_feature_map_cv2(lm_np[i % n_clip], (W, H), sh_np[i % n_clip])
+        cv_ms = (time.perf_counter() - t_cv) / 32 * 1e3
+        extras["e2e_from_landmarks_uint8"] = {
+            "value": n_clip / dtl, "unit": "frames/s", "h2d_bytes_per_step": B * (73 + 18) * 2 * 4, "d2h_bytes_per_step": B * H * W * 3,
+            "rasterise_ms_per_batch": ms_r, "bit_exact_vs_cv2": bool(exact), "cv2_host_ms_per_frame": cv_ms,
+            "api": "ClipRenderer.render_clip_from_landmarks: lspg_draw_feature_maps + lspg_forward_image"}
         one = fm_pool[0][:1].contiguous()
         ms_1 = timed(lambda: net.render(one, cand), 30)
         extras["single_frame"] = {"value": 1e3 / ms_1, "unit": "frames/s", "ms_per_frame": ms_1, "mode": args.mode,

@@ -87,6 +87,17 @@ int lspg_forward_image(lspg_handle h, const float* feature_map, int64_t fm_bstri
                        int64_t cand_bstride, uint8_t* out_hwc, int batch, int height, int width, void* workspace,
                        size_t workspace_bytes, int mode, void* stream);
 
+/* Feature-map rasteriser for a batch of frames ("next" row N2): replaces FaceDataset.get_data_test_mode ->
+ * get_feature_image -> draw_face_feature_maps + draw_shoulder_points (datasets/face_dataset.py:276-323; 72 + 16
+ * cv2.line(img, int(p1), int(p2), 255, 2) calls per frame, then uint8 -> float32 / 255) and the per-frame 1 MB
+ * host->device copy at demo.py:262-265.  Bit-exact with cv2.line (OpenCV 4.13 semantics, see oracle/raster_oracle.py).
+ *   landmarks:  device fp32 [B,73,2] (x,y) in pixels; truncated toward zero like Python int()
+ *   shoulders:  device fp32 [B,n_shoulder_points,2] or NULL (n_shoulder_points even; two polylines of n/2 points)
+ *   out_fm:     device fp32 [B,1,H,W], every element written (0 or 1): ready to be lspg_forward's feature_map
+ * Asynchronous on `stream`. */
+int lspg_draw_feature_maps(lspg_handle h, const float* landmarks, const float* shoulders, int n_shoulder_points,
+                           float* out_fm, int batch, int height, int width, void* stream);
+
 /* Replaces nothing in the reference (module garbage collection). */
 int lspg_destroy(lspg_handle h);
 

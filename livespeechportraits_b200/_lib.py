@@ -11,7 +11,7 @@ LSPG_VARIANT = {"normal": 0, "large": 1}
 LSPG_MODE = {"fast": 0, "parity": 1}
 
 SYMBOLS = [
-    "lspg_create", "lspg_load_weights", "lspg_workspace_bytes", "lspg_forward", "lspg_forward_image", "lspg_destroy",
+    "lspg_create", "lspg_load_weights", "lspg_workspace_bytes", "lspg_forward", "lspg_forward_image", "lspg_draw_feature_maps", "lspg_destroy",
     "lspg_last_error",
     "lspg_num_layers", "lspg_layer_info_get", "lspg_layer_packed", "lspg_layer_affine", "lspg_num_tensors",
     "lspg_tensor_shape", "lspg_debug_read_tensor", "lspg_launches_per_forward", "lspg_flops_per_frame",
@@ -70,6 +70,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     lib.lspg_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int,
                                  C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
     lib.lspg_forward_image.argtypes = lib.lspg_forward.argtypes
+    lib.lspg_draw_feature_maps.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                           C.c_void_p]
     lib.lspg_destroy.argtypes = [C.c_void_p]
     lib.lspg_num_layers.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
     lib.lspg_layer_info_get.argtypes = [C.c_void_p, C.c_int, C.POINTER(LspgLayerInfo)]

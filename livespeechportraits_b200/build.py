@@ -16,7 +16,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "liblspg.so")
 SOURCES = ["lspg.cu"]
-HEADERS = ["conv_umma.cuh", "ptx.cuh", "aux_kernels.cuh", os.path.join("..", "..", "include", "lspg.h")]
+HEADERS = ["conv_umma.cuh", "ptx.cuh", "aux_kernels.cuh", "raster.cuh", os.path.join("..", "..", "include", "lspg.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

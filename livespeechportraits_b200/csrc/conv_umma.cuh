@@ -37,50 +37,80 @@ constexpr int kThreadsWide = 320;        // 2 role warps + 8 epilogue warps (pat
 constexpr int kEpiThreads = 128;
 constexpr int kSmemBudget = 227 * 1024;
 
+// Division by a launch-time constant as multiply-high + shift (dividend < 2^31): decode_tile runs between two tiles of
+// the persistent loops, where ~9 hardware integer divisions cost more than a thousand cycles.
+struct FastDiv {
+  uint32_t mul, shr, d;
+};
+inline FastDiv make_fast_div(uint32_t d) {
+  FastDiv f;
+  f.d = d; f.mul = 0; f.shr = 0;
+  if (d > 1) {
+    uint32_t l = 0;
+    while ((1u << l) < d) ++l;
+    const uint64_t pw = 31 + l;
+    f.mul = static_cast<uint32_t>(((1ull << pw) + d - 1) / d);
+    f.shr = static_cast<uint32_t>(pw - 32);
+  }
+  return f;
+}
+__device__ __forceinline__ int fast_div(int n, const FastDiv& f) {
+  return f.d == 1 ? n : static_cast<int>(__umulhi(static_cast<uint32_t>(n), f.mul) >> f.shr);
+}
+
 struct alignas(64) ConvParams {
-  CUtensorMap a[4];          // activation views: [parity or concat source], dims {C, X, Y, N, limb}
-  CUtensorMap w;             // packed weights, dims {K, Cout_pad, limb*n_phases + phase}
-  CUtensorMap out[4];        // output views per phase, dims {C, X, Y, N, limb}
+  // Field order matters: kernel parameters live in constant bank 0 and are fetched through a small per-SM constant cache
+  // that the three warp roles share.  An ncu source view of the 64-channel layers showed the epilogue's first touch of
+  // each parameter line missing once per tile (6 % of all stall samples on one LDC), so everything the epilogue and the
+  // tile decode read every tile sits in the first two 128-byte lines, the issue/producer scalars and tap tables follow,
+  // and the tensor maps (read by the TMA unit through their generic address, not through the constant cache) come last.
+  // ---- epilogue + tile decode (hot)
   const float* scale;        // folded BatchNorm (or 1/0), [Cout_pad]
   const float* shift;
+  __nv_bfloat16* out_ptr;         // output tensor (NHWC), limb 0; written directly by the epilogue
+  const __nv_bfloat16* res_ptr;   // residual tensor (NHWC, same grid as the output), limb 0; read directly by the epilogue
+  long long out_limb_stride;      // elements between limbs
+  long long res_limb_stride;      // elements between limbs
   float* out_f32;            // tail only: fp32 NCHW [B, 3, 2*hs, 2*ws]
   uint8_t* out_u8;           // tail only, optional: uint8 HWC image [B, 2*hs, 2*ws, 3] = util.tensor2im fused (then out_f32 is unused)
-  __nv_bfloat16* out_ptr;         // output tensor (NHWC), limb 0; written directly by the epilogue
-  long long out_limb_stride;      // elements between limbs
-  int32_t out_channels, out_up;   // out_up: the sampling grid is the source of a folded x2 upsample (phase tc.z -> (2y+py, 2x+px))
-  const __nv_bfloat16* res_ptr;   // residual tensor (NHWC, same grid as the output), limb 0; read directly by the epilogue
-  long long res_limb_stride;      // elements between limbs
-  int32_t res_channels;
-  uint32_t idesc;            // UMMA instruction descriptor (M=128, N=BN, bf16 x bf16 -> f32, K-major)
-  uint32_t idesc2;           // same with N=2*BN (parity patch kernel: stacked [B_hi;B_lo] operand)
-  int32_t n_taps, n_src;
-  int32_t chunks[2];         // 64-channel chunks per concat source
-  int32_t tiles_x, tiles_y, tiles_n;
-  int32_t tw_log2, th_log2;  // tile = TW x TH pixels x NB images, TW*TH*NB = 128
-  int32_t n_tiles;           // Cout_pad / BN
-  int32_t n_phases;
-  int32_t total_tiles;       // tiles_x*tiles_y*tiles_n * n_tiles * n_phases
+  float* partial;            // split-K partial tiles (see n_split)
+  int* split_counter;        // [tiles_per_split] arrival counters (zero between forwards); null = two-pass (finisher kernel)
+  unsigned long long* trace; // debug: per-CTA clock64 stamps (null in production), see kTraceSlots
+  int32_t out_channels, res_channels;
+  int32_t out_up;            // the sampling grid is the source of a folded x2 upsample (phase tc.z -> (2y+py, 2x+px))
   int32_t relu, has_res;
   int32_t batch, hs, ws;     // sampling-grid extent (tail epilogue addressing)
-  int8_t tap_map[4][kMaxTaps];   // [phase][tap] -> index into a[] (added to the concat source index)
-  int8_t tap_dx[4][kMaxTaps];
-  int8_t tap_dy[4][kMaxTaps];
-  // patch mode (conv_patch_kernel): one halo patch {64 ch, patch_w, patch_h} per (tile, source, chunk) whose origin
-  // is the tile origin + (patch_dx0, patch_dy0)[phase]; every tap is a row offset inside the patch.
-  int32_t patch_w, patch_h;
-  int8_t patch_dx0[4], patch_dy0[4];
-  int16_t tap_row[4][kMaxTaps];  // [phase][tap] -> first patch row of the tap's shifted A tile
-  int32_t desc_base_offset;      // 1: set the UMMA descriptor base-offset field from the start address (bring-up switch)
+  int32_t tw_log2, th_log2;  // tile = TW x TH pixels x NB images, TW*TH*NB = 128
+  int32_t total_tiles;       // tiles_x*tiles_y*tiles_n * n_tiles * n_phases * n_split
   // split-K: the K loop (v1: K blocks; patch mode: (source, chunk) items) is cut into n_split ranges of split_len;
   // tile index = split * tiles_per_split + tile.  Each CTA writes its raw fp32 accumulator tile to
   // partial[tile_index][128][BN]; splitk_reduce_kernel sums the splits and applies the epilogue.
-  int32_t n_split, split_len, tiles_per_split;
-  float* partial;
-  int32_t b_resident;            // pair kernel: every weight tile of the layer fits the B ring -> load once per CTA, no streaming
-  int* split_counter;            // [tiles_per_split] arrival counters (zero between forwards); null = two-pass (finisher kernel)
-  unsigned long long* trace;     // debug: per-CTA clock64 stamps (null in production), see kTraceSlots
-  int32_t tap_rotate;            // patch mode: tile (x,y) dependent rotation of the tap order, so that concurrently
-                                 // running CTAs do not all request the same weight tile from L2 at the same time
+  int32_t n_split, tiles_per_split;
+  int32_t n_tiles;           // Cout_pad / BN
+  int32_t tiles_x, tiles_y, tiles_n;
+  int32_t n_phases;
+  int32_t trace_skip;        // debug: the trace records local tiles [trace_skip, trace_skip + kTraceTiles)
+  FastDiv fd_tps, fd_m_tiles, fd_n_tiles, fd_tiles_x, fd_tiles_y;   // divisions of decode_tile (tiles_per_split, ...)
+  // ---- MMA issue + TMA producer
+  uint32_t idesc;            // UMMA instruction descriptor (M=128 or 256, N=BN, bf16 x bf16 -> f32, K-major)
+  uint32_t idesc2;           // same with N=2*BN (parity: stacked [B_hi;B_lo] operand)
+  int32_t n_taps, n_src;
+  int32_t chunks[2];         // 64-channel chunks per concat source
+  int32_t split_len;
+  int32_t b_resident;        // pair kernel: every weight tile of the layer fits the B ring -> load once per CTA, no streaming
+  // patch mode: one halo patch {64 ch, patch_w, patch_h} per (tile, source, chunk) whose origin is the tile origin +
+  // (patch_dx0, patch_dy0)[phase]; every tap is a row offset inside the patch.
+  int32_t patch_w, patch_h;
+  int32_t desc_base_offset;      // 1: set the UMMA descriptor base-offset field from the start address (bring-up switch)
+  int8_t patch_dx0[4], patch_dy0[4];
+  int16_t tap_row[4][kMaxTaps];  // [phase][tap] -> first patch row of the tap's shifted A tile
+  int8_t tap_map[4][kMaxTaps];   // [phase][tap] -> index into a[] (added to the concat source index)
+  int8_t tap_dx[4][kMaxTaps];
+  int8_t tap_dy[4][kMaxTaps];
+  // ---- tensor maps
+  CUtensorMap a[4];          // activation views: [parity or concat source], dims {C, X, Y, N, limb}
+  CUtensorMap w;             // packed weights, dims {K, Cout_pad, limb*n_phases + phase}
+  CUtensorMap out[4];        // output views per phase, dims {C, X, Y, N, limb}
 };
 
 template <int BN, int NL, bool TAIL>
@@ -105,7 +135,7 @@ struct ConvCfg {
 //                   +3 EPI waiting for accumulator, +4 EPI accumulator ready, +5 EPI tile done,
 //                   +6 PROD first B load of the tile issued, +7 PROD last B load issued
 constexpr int kTraceTiles = 12;
-constexpr int kTraceSlots = 4 + 8 * kTraceTiles;
+constexpr int kTraceSlots = 4 + 8 * kTraceTiles + 4;   // tail: [+0] clock64 at kernel exit; slots 2/3: globaltimer (ns) at entry/exit
 __device__ __forceinline__ void trace_stamp(const ConvParams& p, int slot);
 
 struct TileCoord {
@@ -116,28 +146,43 @@ __device__ __forceinline__ void trace_stamp(const ConvParams& p, int slot) {
   if (p.trace != nullptr && slot < kTraceSlots) p.trace[static_cast<size_t>(blockIdx.x) * kTraceSlots + slot] = clock64();
 }
 
+__device__ __forceinline__ void trace_time(const ConvParams& p, bool at_exit) {
+  if (p.trace != nullptr) {
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
+    unsigned long long* t = p.trace + static_cast<size_t>(blockIdx.x) * kTraceSlots;
+    t[at_exit ? 3 : 2] = ns;
+    if (at_exit) t[4 + 8 * kTraceTiles] = clock64();
+  }
+}
+__device__ __forceinline__ void trace_tile(const ConvParams& p, int lt, int k) {
+  if (p.trace != nullptr) {
+    const int i = lt - p.trace_skip;
+    if (i >= 0 && i < kTraceTiles) p.trace[static_cast<size_t>(blockIdx.x) * kTraceSlots + 4 + 8 * i + k] = clock64();
+  }
+}
+
 // The MMA-issuing warp only needs the phase and split index of a tile; for the common single-phase, unsplit layer that
 // is (0, 0) without any integer division (the full decode costs several hundred cycles between two tiles).
 __device__ __forceinline__ void decode_tile_zs(const ConvParams& p, int t, int& z, int& split) {
   if (p.n_phases == 1 && p.n_split == 1) { z = 0; split = 0; return; }
-  split = t / p.tiles_per_split;
+  split = fast_div(t, p.fd_tps);
   t -= split * p.tiles_per_split;
-  z = t / (p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles);
+  z = fast_div(fast_div(t, p.fd_m_tiles), p.fd_n_tiles);
 }
 
 __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int t) {
   TileCoord c;
-  const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
-  c.split = t / p.tiles_per_split;
+  c.split = fast_div(t, p.fd_tps);
   t -= c.split * p.tiles_per_split;
-  int mt = t % m_tiles;
-  int r = t / m_tiles;
-  c.nt = r % p.n_tiles;
-  c.z = r / p.n_tiles;
-  int tx = mt % p.tiles_x;
-  int r2 = mt / p.tiles_x;
-  int ty = r2 % p.tiles_y;
-  int tn = r2 / p.tiles_y;
+  const int r = fast_div(t, p.fd_m_tiles);
+  const int mt = t - r * static_cast<int>(p.fd_m_tiles.d);
+  c.z = fast_div(r, p.fd_n_tiles);
+  c.nt = r - c.z * p.n_tiles;
+  const int r2 = fast_div(mt, p.fd_tiles_x);
+  const int tx = mt - r2 * p.tiles_x;
+  const int tn = fast_div(r2, p.fd_tiles_y);
+  const int ty = r2 - tn * p.tiles_y;
   c.x0 = tx << p.tw_log2;
   c.y0 = ty << p.th_log2;
   c.n0 = tn << (7 - p.tw_log2 - p.th_log2);
@@ -191,33 +236,70 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, uint8_t* /*s
     }
   };
 
-  int lt = 0;
-  for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++lt) {
-    const TileCoord tc = decode_tile(p, t);
-    if (leader) trace_stamp(p, 4 + 8 * lt + 3);
-    // folded BatchNorm parameters of this tile's channel range, double buffered by accumulator index: a warp that
-    // is already on the next tile must not overwrite values a slower warp still reads (no barrier after the math)
-    float* s_scale = s_scale0 + acc * 2 * BN;
-    float* s_shift = s_scale + BN;
-    for (int i = etid; i < BN; i += kEpi) {
-      s_scale[i] = p.scale[tc.nt * BN + i];
-      s_shift[i] = p.shift[tc.nt * BN + i];
+  // Folded BatchNorm parameters of the current N tile, in shared memory.  Tiles are ordered M-fastest, so a CTA's N tile
+  // changes a handful of times per launch (never when Cout = BN): the parameters are re-fetched only then, between two
+  // barriers of the epilogue warps.  No per-tile barrier: TMEM double buffering bounds the skew between the warps.
+  static_assert(BN / 2 <= kEpi, "one 16-byte piece of scale/shift per thread");
+  float* const s_scale = s_scale0;
+  float* const s_shift = s_scale0 + BN;
+  int cur_nt = -1;
+  auto fetch_affine = [&](int nt) {
+    ptx::named_bar_sync(1, kEpi);        // every warp is done with the previous N tile's parameters
+    if (etid < BN / 2) {
+      const bool sh = etid >= BN / 4;
+      const int i = (sh ? etid - BN / 4 : etid) * 4;
+      ptx::cp_async16(s_scale0 + (sh ? BN : 0) + i, (sh ? p.shift : p.scale) + nt * BN + i);
     }
+    ptx::cp_async_wait_all();
+    ptx::named_bar_sync(1, kEpi);
+    cur_nt = nt;
+  };
+  // this thread's pixel inside a tile
+  const int tw_ = row & ((1 << p.tw_log2) - 1);
+  const int th_ = (row >> p.tw_log2) & ((1 << p.th_log2) - 1);
+  const int nb_ = row >> (p.tw_log2 + p.th_log2);
+  // Residual of this thread's pixel: 32 channels x NL limbs per 32-column piece, always requested one piece ahead - the
+  // first piece of a tile while the previous tile is being finished - so that its L2/HBM latency never sits between the
+  // accumulator becoming ready and the TMEM buffer being handed back to the MMA warp.
+  constexpr int kPiecesR = (BN >= 32) ? BN / 32 : 1;
+  const bool use_res = !TAIL && p.has_res && (p.n_split == 1 || p.split_counter != nullptr);
+  uint4 rs[NL][4];
+  auto load_res = [&](const TileCoord& c, int c32) {
+    const int n = c.n0 + nb_, y = c.y0 + th_, x = c.x0 + tw_;
+    const bool ok = n < p.batch && y < p.hs && x < p.ws;
+    // rows outside the image read pixel 0 instead (their result is never stored): no branch around the loads, so the
+    // destination registers stay plain in-flight load targets until the math consumes them
+    const size_t pix = ok ? (static_cast<size_t>(n) * p.hs + y) * p.ws + x : 0;
+    const __nv_bfloat16* rr = p.res_ptr + pix * p.res_channels + c.nt * BN + c32 * 32;
+#pragma unroll
+    for (int l = 0; l < NL; ++l)
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2)
+        ptx::ldg256_nc(rr + l * p.res_limb_stride + h2 * 16, rs[l][2 * h2], rs[l][2 * h2 + 1]);
+  };
+  int lt = 0;
+  TileCoord tc_next = decode_tile(p, blockIdx.x);
+  if (static_cast<int>(blockIdx.x) < p.total_tiles) {
+    if (use_res) load_res(tc_next, grp);
+  }
+  for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++lt) {
+    const TileCoord tc = tc_next;
+    if (leader) trace_tile(p, lt, 3);
     const bool split_mode = !TAIL && p.n_split > 1;
     bool fixup = false;
-    ptx::named_bar_sync(1, kEpi);
+    if (tc.nt != cur_nt) fetch_affine(tc.nt);
+    const int t_next = t + gridDim.x;
+    if (t_next < p.total_tiles) tc_next = decode_tile(p, t_next);
 
-    ptx::mbar_wait(&tfull_bar[acc], acc_phase);
-    ptx::tc_fence_after();
-    if (leader) trace_stamp(p, 4 + 8 * lt + 4);
     constexpr int kAccCols = STACK ? 2 * BN : BN;
     const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccCols;
 
-    const int tw_ = row & ((1 << p.tw_log2) - 1);
-    const int th_ = (row >> p.tw_log2) & ((1 << p.th_log2) - 1);
-    const int nb_ = row >> (p.tw_log2 + p.th_log2);
     const int pn = tc.n0 + nb_, py_ = tc.y0 + th_, px_ = tc.x0 + tw_;
     const bool pix_ok = pn < p.batch && py_ < p.hs && px_ < p.ws;
+
+    ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+    ptx::tc_fence_after();
+    if (leader) trace_tile(p, lt, 4);
 
     if constexpr (TAIL) {
       // ---- tail: 16 columns = 4 phases x 3 channels (+4 pad); tanh; fp32 NCHW scatter or fused tensor2im
@@ -345,40 +427,8 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, uint8_t* /*s
         const int oh = p.out_up ? 2 * p.hs : p.hs, ow = p.out_up ? 2 * p.ws : p.ws;
         const int oy = p.out_up ? 2 * py_ + (tc.z >> 1) : py_, ox = p.out_up ? 2 * px_ + (tc.z & 1) : px_;
         __nv_bfloat16* out_row = p.out_ptr + ((static_cast<size_t>(pn) * oh + oy) * ow + ox) * p.out_channels + tc.nt * BN;
-        const __nv_bfloat16* res_row = p.res_ptr + ((static_cast<size_t>(pn) * p.hs + py_) * p.ws + px_) * p.res_channels +
-                                       tc.nt * BN;
-        if (p.has_res && grp == kGroups - 1) {
-          // pull the residual rows of this CTA's NEXT tile towards L2 while this tile is being finished
-          const int t2 = t + gridDim.x;
-          if (t2 < p.total_tiles) {
-            const TileCoord tc2 = decode_tile(p, t2);
-            const int n2 = tc2.n0 + nb_, y2 = tc2.y0 + th_, x2 = tc2.x0 + tw_;
-            if (n2 < p.batch && y2 < p.hs && x2 < p.ws) {
-              const __nv_bfloat16* r2 = p.res_ptr + ((static_cast<size_t>(n2) * p.hs + y2) * p.ws + x2) * p.res_channels + tc2.nt * BN;
-#pragma unroll
-              for (int l = 0; l < NL; ++l)
-#pragma unroll
-                for (int c = 0; c < BN / 16; ++c)        // every 32-byte sector of the row (a prefetch moves one sector)
-                  asm volatile("prefetch.global.L2 [%0];" ::"l"(r2 + l * p.res_limb_stride + c * 16));
-            }
-          }
-        }
 #pragma unroll 1
         for (int c32 = grp; c32 < kPieces; c32 += kGroups) {
-          uint4 rs[NL][4];                                   // residual: 32 channels x NL limbs of this pixel
-          if (p.has_res) {
-#pragma unroll
-            for (int l = 0; l < NL; ++l)
-#pragma unroll
-              for (int h2 = 0; h2 < 2; ++h2) {
-                if (pix_ok) {
-                  ptx::ldg256_nc(res_row + l * p.res_limb_stride + c32 * 32 + h2 * 16, rs[l][2 * h2], rs[l][2 * h2 + 1]);
-                } else {
-                  rs[l][2 * h2] = make_uint4(0u, 0u, 0u, 0u);
-                  rs[l][2 * h2 + 1] = make_uint4(0u, 0u, 0u, 0u);
-                }
-              }
-          }
           uint32_t vv[32];
           if (fixup) {
             // the summed tile was written back to split 0's slot by the cooperative pass above
@@ -395,14 +445,33 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, uint8_t* /*s
           } else {
             ptx::tmem_ld_32x32(t_acc + c32 * 32, vv);
             if constexpr (STACK) {
-              uint32_t v2[32];
-              ptx::tmem_ld_32x32(t_acc + BN + c32 * 32, v2);
-              ptx::tmem_ld_wait();
+              // second half of the stacked accumulator, 16 columns at a time (register pressure: 168 per thread at 10 warps)
 #pragma unroll
-              for (int i = 0; i < 32; ++i) vv[i] = __float_as_uint(__uint_as_float(vv[i]) + __uint_as_float(v2[i]));
+              for (int hh = 0; hh < 2; ++hh) {
+                uint32_t v2[16];
+                ptx::tmem_ld_32x16(t_acc + BN + c32 * 32 + hh * 16, v2);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) vv[hh * 16 + i] = __float_as_uint(__uint_as_float(vv[hh * 16 + i]) + __uint_as_float(v2[i]));
+              }
             }
             ptx::tmem_ld_wait();
             if (c32 + kGroups >= kPieces) release_tmem();   // this warp's share of the accumulator is in registers
+          }
+          // this piece's residual was requested one piece ahead.  A warp with several pieces per tile keeps two register
+          // sets (the next request is issued before the math); with one piece per tile the next request - the next TILE's
+          // residual, a whole tile period ahead of its use - is issued after the math into the same registers.
+          constexpr bool kDoubleRes = (kPieces / kGroups) > 1;
+          uint4 rc[NL][4];
+          if (use_res) {
+#pragma unroll
+            for (int l = 0; l < NL; ++l)
+#pragma unroll
+              for (int e = 0; e < 4; ++e) rc[l][e] = rs[l][e];
+            if constexpr (kDoubleRes) {
+              if (c32 + kGroups < kPieces) load_res(tc, c32 + kGroups);
+              else if (t_next < p.total_tiles) load_res(tc_next, grp);
+            }
           }
           uint4 o_prev = make_uint4(0u, 0u, 0u, 0u), ol_prev = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
@@ -416,7 +485,7 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, uint8_t* /*s
             if (p.has_res) {
 #pragma unroll
               for (int l = 0; l < NL; ++l) {
-                const uint32_t rr[4] = {rs[l][piece].x, rs[l][piece].y, rs[l][piece].z, rs[l][piece].w};
+                const uint32_t rr[4] = {rc[l][piece].x, rc[l][piece].y, rc[l][piece].z, rc[l][piece].w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   y[2 * e] += bf16_lo(rr[e]);
@@ -452,10 +521,13 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, uint8_t* /*s
               ol_prev = ol;
             }
           }
+          if constexpr (!kDoubleRes) {
+            if (use_res && t_next < p.total_tiles) load_res(tc_next, grp);
+          }
         }
       }
     }
-    if (leader) trace_stamp(p, 4 + 8 * lt + 5);
+    if (leader) trace_tile(p, lt, 5);
     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
   }
 }
@@ -748,7 +820,7 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) conv_patch_kernel(const __gri
       const TileCoord tc = decode_tile(p, t);
       const int ci0 = tc.split * p.split_len;
       const int ci1 = (ci0 + p.split_len < kb_per_tap) ? ci0 + p.split_len : kb_per_tap;
-      if (lane == 0) trace_stamp(p, 4 + 8 * lt + 6);
+      if (lane == 0) trace_tile(p, lt, 6);
       for (int ci = ci0; ci < ci1; ++ci) {
         for (int g = 0; g < n_groups; ++g) {
           ptx::mbar_wait(&bempty_bar[ib], phb ^ 1);
@@ -783,7 +855,7 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) conv_patch_kernel(const __gri
           if (g == a_after_group) issue_a();
         }
       }
-      if (lane == 0) trace_stamp(p, 4 + 8 * lt + 7);
+      if (lane == 0) trace_tile(p, lt, 7);
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
@@ -801,7 +873,7 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) conv_patch_kernel(const __gri
       decode_tile_zs(p, t, tc.z, tc.split);
       ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       ptx::tc_fence_after();
-      if (lane == 0) trace_stamp(p, 4 + 8 * lt + 0);
+      if (lane == 0) trace_tile(p, lt, 0);
       const uint32_t d_tmem = tmem_base + acc * Cfg::kAccCols;
       const int ci0 = tc.split * p.split_len;
       const int ci1 = (ci0 + p.split_len < kb_per_tap) ? ci0 + p.split_len : kb_per_tap;
@@ -811,7 +883,7 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) conv_patch_kernel(const __gri
         for (int g = 0; g < n_groups; ++g) {
           if (!b_ready) ptx::mbar_wait(&bfull_bar[ib], phb);
           ptx::tc_fence_after();
-          if (lane == 0 && ci == ci0 && g == 0) trace_stamp(p, 4 + 8 * lt + 1);
+          if (lane == 0 && ci == ci0 && g == 0) trace_tile(p, lt, 1);
           const int tap0 = g * Cfg::kTPS;
           const int tap1 = (tap0 + Cfg::kTPS < p.n_taps) ? tap0 + Cfg::kTPS : p.n_taps;
           if (ptx::elect_one()) {
@@ -847,7 +919,7 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) conv_patch_kernel(const __gri
         }
         if (++ia == Cfg::kAStages) { ia = 0; pha ^= 1; }
       }
-      if (lane == 0) trace_stamp(p, 4 + 8 * lt + 2);
+      if (lane == 0) trace_tile(p, lt, 2);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
@@ -873,27 +945,33 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) conv_patch_kernel(const __gri
 // single-CTA kernel, halves the L2->SM weight traffic and doubles the ring depth per byte.
 // PARITY (NL = 2) issues hi*hi, hi*lo, lo*hi as three N = BN MMAs (B_hi and B_lo are each split across the pair).
 // ====================================================================================================
-template <int BN, int NL>
+// STK (parity, N tile 64): the stage of CTA r holds X = limb r of the whole 64-row tile (so that the pair's X tiles form the
+// stacked [B_hi; B_lo] operand of one N = 128 MMA: A_hi*B_hi | A_hi*B_lo) and Y = rows [32r, 32r+32) of B_hi (the pair's
+// Y tiles form B_hi for the N = 64 MMA A_lo*B_hi).  Two MMAs instead of three per K step and 11 KB instead of 15 KB of
+// operand reads per SM: the N = 64 layers are bound by shared-memory bandwidth (A is re-read for every 64 columns).
+template <int BN, int NL, bool STK = false>
 struct PairCfg {
+  static_assert(!STK || (NL == 2 && BN == 64), "stacked operands: parity mode, N tile 64");
   static constexpr int kBHalf = (BN / 2) * 128;                   // bytes of this CTA's half of one B tile
   static constexpr int kAStage = NL * kPatchStride;
-  static constexpr int kBStage = NL * kBHalf;                     // one tap per stage
+  static constexpr int kBStage = STK ? 3 * kBHalf : NL * kBHalf;  // one tap per stage
+  static constexpr int kAccCols = STK ? 2 * BN : BN;
   static constexpr int kAStages = 2;
   static constexpr int kAux = 5120;
   static constexpr int kAvail = kSmemBudget - 1024 - kAux - kAStages * kAStage;
   static constexpr int kBStagesRaw = kAvail / kBStage;
   static constexpr int kBStages = kBStagesRaw > 16 ? 16 : kBStagesRaw;
   static constexpr int kSmemBytes = 1024 + kAStages * kAStage + kBStages * kBStage + kAux;
-  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kTmemCols = 2 * kAccCols;
   static_assert(BN == 64 || BN == 128 || BN == 256, "pair kernel: N tile 64, 128 or 256");
   static_assert(kTmemCols <= 512, "TMEM has 512 columns");
   static_assert(kBStages >= 3, "B ring too shallow");
   static_assert(4 * BN * 4 + (2 * 16 + 2 * 2 + 8) * 8 <= kAux, "aux region too small");
 };
 
-template <int BN, int NL, int EW>
+template <int BN, int NL, int EW, bool STK = false>
 __global__ void __launch_bounds__(64 + EW * 32, 1) conv_pair_kernel(const __grid_constant__ ConvParams p) {
-  using Cfg = PairCfg<BN, NL>;
+  using Cfg = PairCfg<BN, NL, STK>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_ring = smem;
@@ -915,6 +993,7 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) conv_pair_kernel(const __grid
   const int lane = threadIdx.x & 31;
   const uint32_t crank = ptx::cluster_ctarank();
   const bool leader_cta = (crank == 0);
+  if (threadIdx.x == 0) { trace_stamp(p, 0); trace_time(p, false); }
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 4; ++i) ptx::prefetch_tmap(&p.a[i]);
@@ -938,6 +1017,7 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) conv_pair_kernel(const __grid
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   ptx::pdl_launch_dependents();
+  if (threadIdx.x == 0) trace_stamp(p, 1);
 
   int kb_per_tap = 0;
   for (int s = 0; s < p.n_src; ++s) kb_per_tap += p.chunks[s];
@@ -949,13 +1029,14 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) conv_pair_kernel(const __grid
     ptx::pdl_wait();
     int ia = 0, ib = 0;
     uint32_t pha = 0, phb = 0;
-    int a_tile = blockIdx.x, a_ci = 0;
+    int a_tile = blockIdx.x, a_ci = 0, a_lt = 0;
     auto issue_a = [&]() {
       if (a_tile >= p.total_tiles) return;
       const TileCoord tc = decode_tile(p, a_tile);
       const int s = (a_ci < p.chunks[0]) ? 0 : 1;
       const int c = (s == 0) ? a_ci : a_ci - p.chunks[0];
       ptx::mbar_wait(&aempty_bar[ia], pha ^ 1);
+      if (lane == 0 && a_ci == 0) trace_tile(p, a_lt, 6);
       if (ptx::elect_one()) {
         if (leader_cta) ptx::mbar_expect_tx(&afull_bar[ia], 2 * NL * patch_bytes);     // both CTAs' patches
 #pragma unroll
@@ -965,7 +1046,25 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) conv_pair_kernel(const __grid
       }
       __syncwarp();
       if (++ia == Cfg::kAStages) { ia = 0; pha ^= 1; }
-      if (++a_ci == kb_per_tap) { a_ci = 0; a_tile += gridDim.x; }
+      if (++a_ci == kb_per_tap) {
+        if (lane == 0) trace_tile(p, a_lt, 7);
+        a_ci = 0; a_tile += gridDim.x; ++a_lt;
+      }
+    };
+    // this CTA's share of one weight tile (K chunk ci, tap, phase z, N tile nt) -> dst, completing on the leader's `bar`
+    auto load_b = [&](uint8_t* dst, uint64_t* bar, int ci, int nt, int tap, int z) {
+      if constexpr (STK) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h)      // X: limb `crank` of the whole tile, as two boxes of BN/2 rows
+          ptx::tma_load_4d_pair(&p.w, bar, dst + h * Cfg::kBHalf, ci * kChunk, nt * BN + h * (BN / 2), tap,
+                                static_cast<int>(crank) * p.n_phases + z);
+        ptx::tma_load_4d_pair(&p.w, bar, dst + 2 * Cfg::kBHalf, ci * kChunk, nt * BN + static_cast<int>(crank) * (BN / 2), tap, z);
+      } else {
+#pragma unroll
+        for (int l = 0; l < NL; ++l)     // rows [crank*BN/2, +BN/2) of every limb
+          ptx::tma_load_4d_pair(&p.w, bar, dst + l * Cfg::kBHalf, ci * kChunk, nt * BN + static_cast<int>(crank) * (BN / 2), tap,
+                                l * p.n_phases + z);
+      }
     };
     if (p.b_resident) {
       // all weight tiles of the layer (this CTA's half of each) are loaded once; one barrier covers them
@@ -976,10 +1075,7 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) conv_pair_kernel(const __grid
           if (leader_cta) ptx::mbar_expect_tx(&bfull_bar[0], 2 * n_items * Cfg::kBStage);
           for (int ci = 0; ci < kb_per_tap; ++ci)
             for (int tap = 0; tap < p.n_taps; ++tap)
-#pragma unroll
-              for (int l = 0; l < NL; ++l)
-                ptx::tma_load_4d_pair(&p.w, &bfull_bar[0], b_ring + (ci * p.n_taps + tap) * Cfg::kBStage + l * Cfg::kBHalf,
-                                      ci * kChunk, tc.nt * BN + static_cast<int>(crank) * (BN / 2), tap, l * p.n_phases + tc.z);
+              load_b(b_ring + (ci * p.n_taps + tap) * Cfg::kBStage, &bfull_bar[0], ci, tc.nt, tap, tc.z);
         }
         __syncwarp();
       }
@@ -997,11 +1093,8 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) conv_pair_kernel(const __grid
           ptx::mbar_wait(&bempty_bar[ib], phb ^ 1);
           if (ptx::elect_one()) {
             uint8_t* st = b_ring + ib * Cfg::kBStage;
-            if (leader_cta) ptx::mbar_expect_tx(&bfull_bar[ib], 2 * Cfg::kBStage);    // both halves
-#pragma unroll
-            for (int l = 0; l < NL; ++l)     // this CTA's half of the tile: rows [crank*BN/2, +BN/2)
-              ptx::tma_load_4d_pair(&p.w, &bfull_bar[ib], st + l * Cfg::kBHalf, ci * kChunk,
-                                    tc.nt * BN + static_cast<int>(crank) * (BN / 2), tap, l * p.n_phases + tc.z);
+            if (leader_cta) ptx::mbar_expect_tx(&bfull_bar[ib], 2 * Cfg::kBStage);    // both CTAs' shares
+            load_b(st, &bfull_bar[ib], ci, tc.nt, tap, tc.z);
           }
           __syncwarp();
           if (++ib == Cfg::kBStages) { ib = 0; phb ^= 1; }
@@ -1020,14 +1113,17 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) conv_pair_kernel(const __grid
       bool b_ready = false;
       const bool resident = p.b_resident != 0;
       if (resident && blockIdx.x < p.total_tiles) { ptx::mbar_wait(&bfull_bar[0], 0); b_ready = true; }
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      int lt = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++lt) {
         int z, split;
         decode_tile_zs(p, t, z, split);
         ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        if (lane == 0) trace_tile(p, lt, 0);
+        const uint32_t d_tmem = tmem_base + acc * Cfg::kAccCols;
         for (int ci = 0; ci < kb_per_tap; ++ci) {
           ptx::mbar_wait(&afull_bar[ia], pha);
+          if (lane == 0 && ci == 0) trace_tile(p, lt, 1);
           const uint32_t a0 = ptx::smem_u32(a_ring + ia * Cfg::kAStage);
           for (int tap = 0; tap < p.n_taps; ++tap) {
             if (!b_ready) ptx::mbar_wait(&bfull_bar[ib], phb);
@@ -1040,12 +1136,19 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) conv_pair_kernel(const __grid
 #pragma unroll
               for (int k = 0; k < kChunk / 16; ++k) {
                 const uint32_t accum = (ci > 0 || tap > 0 || k > 0) ? 1u : 0u;
+                if constexpr (STK) {
+                  const uint64_t a_lo = umma_desc_sw128_strided(a_hi_addr + kPatchStride, sbo, false);
+                  const uint64_t b_y = ptx::umma_desc_sw128(b0 + 2 * Cfg::kBHalf);
+                  ptx::umma_f16_pair(d_tmem, a_hi + 2 * k, b_hi + 2 * k, p.idesc2, accum);   // N = 2*BN: A_hi*[B_hi | B_lo]
+                  ptx::umma_f16_pair(d_tmem, a_lo + 2 * k, b_y + 2 * k, p.idesc, 1u);        // N = BN:   A_lo*B_hi
+                } else {
                 ptx::umma_f16_pair(d_tmem, a_hi + 2 * k, b_hi + 2 * k, p.idesc, accum);
                 if (NL == 2) {
                   const uint64_t a_lo = umma_desc_sw128_strided(a_hi_addr + kPatchStride, sbo, false);
                   const uint64_t b_lo = ptx::umma_desc_sw128(b0 + Cfg::kBHalf);
                   ptx::umma_f16_pair(d_tmem, a_hi + 2 * k, b_lo + 2 * k, p.idesc, 1u);
                   ptx::umma_f16_pair(d_tmem, a_lo + 2 * k, b_hi + 2 * k, p.idesc, 1u);
+                }
                 }
               }
               if (!resident) ptx::umma_commit_pair(&bempty_bar[ib], kMask);
@@ -1062,15 +1165,17 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) conv_pair_kernel(const __grid
           }
           if (++ia == Cfg::kAStages) { ia = 0; pha ^= 1; }
         }
+        if (lane == 0) trace_tile(p, lt, 2);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else {
-    epilogue_warps<BN, NL, false, 0, false, true, EW>(p, aux, s_scale, s_shift, tfull_bar, tempty_bar, stg_bar, tmem_base, warp, lane);
+    epilogue_warps<BN, NL, false, 0, STK, true, EW>(p, aux, s_scale, s_shift, tfull_bar, tempty_bar, stg_bar, tmem_base, warp, lane);
   }
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) trace_time(p, true);
   ptx::cluster_sync();
   if (warp == 1) {
     ptx::tc_fence_after();

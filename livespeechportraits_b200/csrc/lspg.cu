@@ -22,6 +22,7 @@
 
 #include "../../include/lspg.h"
 #include "aux_kernels.cuh"
+#include "raster.cuh"
 #include "conv_umma.cuh"
 
 namespace {
@@ -423,6 +424,12 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 int nl_of(int mode) { return mode == LSPG_MODE_PARITY ? 2 : 1; }
 
+// conv_pair_kernel variant with stacked [B_hi; B_lo] operands (parity mode, N tile 64); see PairCfg
+bool pair_stacked(int bn, int NL) {
+  static const bool off = getenv("LSPG_NO_PAIR_STACK") != nullptr;
+  return !off && bn == 64 && NL == 2;
+}
+
 size_t tensor_bytes_one_limb(const TensorInfo& t, int B, int H, int W) {
   return static_cast<size_t>(B) * (H >> t.shift) * (W >> t.shift) * t.channels * 2;
 }
@@ -460,8 +467,12 @@ Geo layer_geo(const lspg_ctx* h, const Layer& L, int B, int H, int W) {
   g.m_tiles = (g.ws / g.tw) * (g.hs / g.th) * ((B + g.nb - 1) / g.nb);
   const int chunks = L.cin[0] / 64 + (L.n_src == 2 ? L.cin[1] / 64 : 0);
   g.k_items = g.patch ? chunks : chunks * L.n_taps;
+  static const bool small_bn128 = getenv("LSPG_SMALL_BN128") != nullptr;
   if (L.kind == K_TAIL) g.bn = 16;
   else g.bn = (L.cout_pad % 128 == 0 && g.m_tiles * (L.cout_pad / 128) * L.n_phases >= h->num_sms_or_default()) ? 128 : 64;
+  // per-tap kernel below 16^2: the N=128 tile halves the A traffic per MAC (the kernel is shared-memory bound) and split-K
+  // restores the CTA count
+  if (small_bn128 && !g.patch && L.kind != K_TAIL && L.cout_pad % 128 == 0 && g.m_tiles >= 8) g.bn = 128;
   // CTA-pair kernel for the wide layers: N tile 256 (or 128), two neighbouring M tiles per cluster
   static const bool no_pair = getenv("LSPG_NO_PAIR") != nullptr;
   g.pair = false;
@@ -482,7 +493,8 @@ Geo layer_geo(const lspg_ctx* h, const Layer& L, int B, int H, int W) {
   const int sms = h->num_sms_or_default();
   if (!no_split && !g.pair && L.kind != K_TAIL && g.tiles_per_split * 2 <= sms) {
     const int min_len = g.patch ? 1 : 4;                       // at least 4 K blocks (v1) / 1 chunk of all taps per split
-    int want = (sms + g.tiles_per_split - 1) / g.tiles_per_split;
+    static const bool split_floor = getenv("LSPG_SPLIT_FLOOR") != nullptr;
+    int want = split_floor ? sms / g.tiles_per_split : (sms + g.tiles_per_split - 1) / g.tiles_per_split;   // floor: one wave
     int max_split = g.k_items / min_len;
     if (max_split < 1) max_split = 1;
     if (want > max_split) want = max_split;
@@ -598,11 +610,6 @@ uint32_t make_idesc(int bn, int m = kTileM) {
   return d;
 }
 
-int choose_bn(const Layer& L) {
-  if (L.kind == K_TAIL) return 16;
-  return (L.cout_pad % 128 == 0) ? 128 : 64;
-}
-
 int build_plan(lspg_ctx* h, Plan* P, int B, int H, int W, int mode, void* workspace) {
   const int NL = nl_of(mode);
   P->batch = B; P->height = H; P->width = W; P->mode = mode; P->workspace = workspace;
@@ -646,8 +653,6 @@ int build_plan(lspg_ctx* h, Plan* P, int B, int H, int W, int mode, void* worksp
         for (int t = 0; t < L.n_taps; ++t)
           p.tap_row[z][t] = static_cast<int16_t>((L.tap_dy[z][t] - p.patch_dy0[z]) * pw + (L.tap_dx[z][t] - p.patch_dx0[z]));
       p.desc_base_offset = no_base_offset ? 0 : 1;
-      static const bool tap_rotate = getenv("LSPG_TAP_ROTATE") != nullptr;
-      p.tap_rotate = tap_rotate ? 1 : 0;
       if (pw * ph * 128 > kPatchSlot) return fail(LSPG_EINVAL, "patch %dx%d does not fit its smem slot", pw, ph);
       abox_w = pw; abox_h = ph; abox_n = 1;
     }
@@ -657,12 +662,17 @@ int build_plan(lspg_ctx* h, Plan* P, int B, int H, int W, int mode, void* worksp
     p.n_tiles = L.cout_pad / pl.bn;
     p.n_phases = L.n_phases;
     p.tiles_per_split = g.tiles_per_split;
+    p.fd_tps = make_fast_div(g.tiles_per_split);
+    p.fd_m_tiles = make_fast_div(p.tiles_x * p.tiles_y * p.tiles_n);
+    p.fd_n_tiles = make_fast_div(p.n_tiles);
+    p.fd_tiles_x = make_fast_div(p.tiles_x);
+    p.fd_tiles_y = make_fast_div(p.tiles_y);
     p.n_split = g.n_split; p.split_len = g.split_len;
     p.total_tiles = g.tiles_per_split * g.n_split;
     if (g.pair) {
       static const bool no_resident = getenv("LSPG_NO_RESIDENT") != nullptr;
       const int n_items = g.k_items * L.n_taps;                           // weight tiles per output tile
-      const int stage = NL * (g.bn / 2) * 128;
+      const int stage = (pair_stacked(g.bn, NL) ? 3 : NL) * (g.bn / 2) * 128;
       const int cap = std::min(16, (kSmemBudget - 1024 - 5120 - 2 * NL * kPatchStride) / stage);
       p.b_resident = (!no_resident && L.n_phases == 1 && g.n_tiles == 1 && n_items <= cap) ? 1 : 0;
     }
@@ -679,7 +689,7 @@ int build_plan(lspg_ctx* h, Plan* P, int B, int H, int W, int mode, void* worksp
     p.relu = L.relu; p.has_res = L.res >= 0 ? 1 : 0;
     p.batch = B; p.hs = Hs; p.ws = Ws;
     p.idesc = g.pair ? make_idesc(pl.bn, 256) : make_idesc(pl.bn);
-    p.idesc2 = make_idesc(2 * pl.bn > 256 ? 256 : 2 * pl.bn);
+    p.idesc2 = g.pair ? make_idesc(2 * pl.bn > 256 ? 256 : 2 * pl.bn, 256) : make_idesc(2 * pl.bn > 256 ? 256 : 2 * pl.bn);
     p.scale = L.d_scale; p.shift = L.d_shift; p.out_f32 = nullptr;
     memcpy(p.tap_map, L.tap_map, sizeof(p.tap_map));
     memcpy(p.tap_dx, L.tap_dx, sizeof(p.tap_dx));
@@ -745,6 +755,8 @@ int build_plan(lspg_ctx* h, Plan* P, int B, int H, int W, int mode, void* worksp
         if (!h->trace_buf) CUDA_TRY(cudaMalloc(&h->trace_buf, sizeof(unsigned long long) * 256 * kTraceSlots));
         CUDA_TRY(cudaMemset(h->trace_buf, 0, sizeof(unsigned long long) * 256 * kTraceSlots));
         p.trace = h->trace_buf;
+        const char* ts = getenv("LSPG_TRACE_SKIP");
+        p.trace_skip = ts ? atoi(ts) : 0;
       }
     }
     if (pl.split) {
@@ -838,20 +850,23 @@ int launch_patch_cl(const ConvParams& p, int grid, int cluster, cudaStream_t st)
   return cluster == 2 ? launch_patch<BN, NL, TAIL, 2, (TAIL ? 4 : 8)>(p, grid, st) : launch_patch<BN, NL, TAIL, 1, (TAIL ? 4 : 8)>(p, grid, st);
 }
 
-template <int BN, int NL, int EW>
+template <int BN, int NL, int EW, bool STK = false>
 int launch_pair_ew(const ConvParams& p, int grid, cudaStream_t st) {
-  using Cfg = PairCfg<BN, NL>;
+  using Cfg = PairCfg<BN, NL, STK>;
   static bool configured = false;
   if (!configured) {
-    CUDA_TRY(cudaFuncSetAttribute(conv_pair_kernel<BN, NL, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    CUDA_TRY(cudaFuncSetAttribute(conv_pair_kernel<BN, NL, EW, STK>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
-  CUDA_TRY(launch_pdl_cluster(conv_pair_kernel<BN, NL, EW>, dim3(grid), dim3(64 + EW * 32), Cfg::kSmemBytes, st, 2, p));
+  CUDA_TRY(launch_pdl_cluster(conv_pair_kernel<BN, NL, EW, STK>, dim3(grid), dim3(64 + EW * 32), Cfg::kSmemBytes, st, 2, p));
   return LSPG_OK;
 }
 
 template <int BN, int NL>
 int launch_pair(const ConvParams& p, int grid, cudaStream_t st) {
+  if constexpr (BN == 64 && NL == 2) {
+    if (pair_stacked(BN, NL)) return launch_pair_ew<BN, NL, 8, true>(p, grid, st);
+  }
   return epi_warps() == 4 ? launch_pair_ew<BN, NL, 4>(p, grid, st) : launch_pair_ew<BN, NL, 8>(p, grid, st);
 }
 
@@ -1113,6 +1128,25 @@ int lspg_forward_image(lspg_handle h, const float* feature_map, int64_t fm_bstri
                        int mode, void* stream) {
   return forward_impl(h, feature_map, fm_bstride, cand, cand_bstride, out_hwc, 1, batch, height, width, workspace,
                       workspace_bytes_in, mode, stream);
+}
+
+int lspg_draw_feature_maps(lspg_handle h, const float* landmarks, const float* shoulders, int n_shoulder_points, float* out_fm,
+                           int batch, int height, int width, void* stream) {
+  if (!h || !landmarks || !out_fm) return fail(LSPG_EINVAL, "null argument");
+  if (batch <= 0 || height <= 0 || width <= 0) return fail(LSPG_EINVAL, "bad shape %d x %d x %d", batch, height, width);
+  if (shoulders != nullptr && (n_shoulder_points < 0 || n_shoulder_points % 2 != 0))
+    return fail(LSPG_EINVAL, "n_shoulder_points must be even (two polylines), got %d", n_shoulder_points);
+  if (h->device < 0) return fail(LSPG_ENODEV, "host-only handle: lspg_draw_feature_maps needs an sm_100 device (no CPU path exists)");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(cudaMemsetAsync(out_fm, 0, sizeof(float) * static_cast<size_t>(batch) * height * width, st));
+  const int n_sh = shoulders ? n_shoulder_points : 0;
+  const int segs = kFaceSegments + (n_sh / 2 > 1 ? 2 * (n_sh / 2 - 1) : 0);
+  const int threads = 32;                       // one warp per block: the segments of a frame spread over several SMs
+  raster_feature_maps_kernel<<<dim3((segs + threads - 1) / threads, batch), threads, 0, st>>>(landmarks, shoulders, n_sh, out_fm,
+                                                                                            height, width);
+  CUDA_TRY(cudaGetLastError());
+  return LSPG_OK;
 }
 
 // ---------------------------------------------------------------------------------------- introspection

@@ -216,6 +216,36 @@ class Feature2Face_G(nn.Module):
         del hold
         return out
 
+    def draw_feature_maps(self, landmarks: torch.Tensor, shoulders: Optional[torch.Tensor] = None,
+                          size: tuple = (512, 512), out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Rasterise a clip's landmark tracks into the ``[B,1,H,W]`` {0,1} maps ``render`` consumes, on the GPU.
+
+        Batched replacement of ``FaceDataset.get_data_test_mode`` (datasets/face_dataset.py:276-323; 88 ``cv2.line`` calls and
+        a 1 MB host->device copy per frame at demo.py:262-265), bit-exact with cv2.  ``landmarks`` ``[B,73,2]`` and
+        ``shoulders`` ``[B,2k,2]`` (or None) are fp32 CUDA tensors in pixel coordinates; ``size`` is ``(W, H)`` like the
+        reference's ``(opt.loadSize, opt.loadSize)``."""
+        if landmarks.dtype != torch.float32 or landmarks.dim() != 3 or landmarks.shape[1:] != (73, 2):
+            raise ValueError(f"landmarks must be fp32 [B,73,2], got {landmarks.dtype} {tuple(landmarks.shape)}")
+        self._ensure_handle(landmarks.device)
+        b = landmarks.shape[0]
+        w, h = int(size[0]), int(size[1])
+        lm = landmarks.contiguous()
+        sh, n_sh = None, 0
+        if shoulders is not None:
+            if shoulders.dtype != torch.float32 or shoulders.dim() != 3 or shoulders.shape[0] != b or shoulders.shape[2] != 2 \
+                    or shoulders.shape[1] % 2 or shoulders.device != landmarks.device:
+                raise ValueError(f"shoulders must be fp32 [B,2k,2] on the landmarks' device, got {tuple(shoulders.shape)}")
+            sh, n_sh = shoulders.contiguous(), shoulders.shape[1]
+        if out is None:
+            out = torch.empty((b, 1, h, w), dtype=torch.float32, device=landmarks.device)
+        elif tuple(out.shape) != (b, 1, h, w) or out.dtype != torch.float32 or not out.is_contiguous():
+            raise ValueError(f"out must be a contiguous fp32 tensor of shape {(b, 1, h, w)}")
+        stream = torch.cuda.current_stream(landmarks.device).cuda_stream
+        _lib.check(self._lib.lspg_draw_feature_maps(self._handle, lm.data_ptr(), sh.data_ptr() if sh is not None else None, n_sh,
+                                                    out.data_ptr(), b, h, w, stream))
+        del lm, sh
+        return out
+
     def forward(self, input: torch.Tensor) -> torch.Tensor:  # noqa: A002 - reference argument name
         return self.render(input, None)
 

@@ -35,6 +35,47 @@ class ClipRenderer:
             self._out = [torch.empty(oshape, dtype=odt, device=self.device) for _ in range(2)]
         return self._fm, self._out
 
+    def render_clip_from_landmarks(self, landmarks_host: torch.Tensor, shoulders_host: Optional[torch.Tensor],
+                                   cand_device: torch.Tensor, out_host: torch.Tensor, size: tuple = (512, 512)) -> torch.Tensor:
+        """Same loop with the feature maps drawn on the GPU (``Feature2Face_G.draw_feature_maps``, the batched replacement of
+        datasets/face_dataset.py:276-323): per frame 728 bytes of landmark / shoulder tracks cross PCIe instead of a 1 MB map.
+        ``landmarks_host`` [N,73,2] and ``shoulders_host`` [N,2k,2] (or None) are fp32; the whole clip's tracks (a few hundred
+        KB) are uploaded once, batches are rasterised on the compute stream right before their generator pass."""
+        n = landmarks_host.shape[0]
+        w, h = int(size[0]), int(size[1])
+        if tuple(out_host.shape) != ((n, h, w, 3) if self.uint8 else (n, 3, h, w)) or not out_host.is_pinned():
+            raise ValueError("out_host must be pinned [N,3,H,W] fp32 (or [N,H,W,3] uint8 with uint8=True)")
+        fm_dev, out_dev = self._staging(h, w)
+        caller = torch.cuda.current_stream(self.device)
+        for s in (self._compute, self._d2h):
+            s.wait_stream(caller)
+        per_frame_cand = cand_device.shape[0] == n and n > 1
+        d2h_done = [None, None]
+        with torch.cuda.stream(self._compute):
+            lm_dev = landmarks_host.to(self.device, non_blocking=True)
+            sh_dev = shoulders_host.to(self.device, non_blocking=True) if shoulders_host is not None else None
+        for bi, off in enumerate(range(0, n, self.batch)):
+            ln = min(self.batch, n - off)
+            j = bi & 1
+            with torch.cuda.stream(self._compute):
+                if d2h_done[j] is not None:
+                    self._compute.wait_event(d2h_done[j])        # previous frames of this buffer are on the host
+                self.net.draw_feature_maps(lm_dev[off:off + ln], None if sh_dev is None else sh_dev[off:off + ln], (w, h),
+                                           out=fm_dev[j][:ln])
+                cd = cand_device[off:off + ln] if per_frame_cand else cand_device[:1]
+                self.net.render(fm_dev[j][:ln], cd, out=out_dev[j][:ln], precision=self.precision, _uint8=self.uint8)
+                ev = torch.cuda.Event()
+                ev.record(self._compute)
+            with torch.cuda.stream(self._d2h):
+                self._d2h.wait_event(ev)
+                out_host[off:off + ln].copy_(out_dev[j][:ln], non_blocking=True)
+                dn = torch.cuda.Event()
+                dn.record(self._d2h)
+                d2h_done[j] = dn
+        self._d2h.synchronize()
+        caller.wait_stream(self._compute)
+        return out_host
+
     def render_clip(self, feature_maps_host: torch.Tensor, cand_device: torch.Tensor, out_host: torch.Tensor) -> torch.Tensor:
         """``feature_maps_host`` [N,1,H,W] fp32 (pinned), ``cand_device`` [1|N,12,H,W] on the GPU (demo.py:95 moves the
         candidates once per clip), ``out_host`` [N,3,H,W] fp32 (pinned).  Returns ``out_host`` after the last copy

