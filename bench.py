@@ -37,7 +37,7 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--mode", default="parity", choices=["parity", "fast"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--variant", default="large", choices=["large", "normal"],
@@ -310,7 +310,7 @@ def main():
     }
 
     # ---- end to end through the public batched API: pinned host feature maps in, pinned host frames out
-    Ke = min(K, 40)                                   # clip length of the end-to-end leg (bounds the pinned host buffers)
+    Ke = min(K, 20)                                   # clip length of the end-to-end leg (bounds the pinned host buffers)
     n_clip = B * Ke
     fm_host = torch.empty((n_clip, 1, H, W), dtype=torch.float32, pin_memory=True)
     for i in range(Ke):

@@ -210,7 +210,7 @@ struct StgCfg {
 // EW = number of epilogue warps (4 or 8).  A warp may read TMEM lane quarter (warp % 4); with EW = 8 two warps share a
 // quarter and split the columns in interleaved 32-column pieces, which doubles the loads/stores in flight and the issue
 // slots of the epilogue (the 64-channel layers were epilogue-bound with 4 warps: 6.2k cycles vs 3.5k of MMAs per tile).
-template <int BN, int NL, bool TAIL, int NSTG, bool STACK, bool PAIR = false, int EW = 4>
+template <int BN, int NL, bool TAIL, int NSTG, bool STACK, bool PAIR = false, int EW = 4, int NACC = 2>
 __device__ __forceinline__ void epilogue_warps(const ConvParams& p, uint8_t* /*stg_base*/, float* s_scale0, float* /*unused*/,
                                                uint64_t* tfull_bar, uint64_t* tempty_bar, uint64_t* stg_bar,
                                                uint32_t tmem_base, int warp, int lane) {
@@ -528,7 +528,7 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, uint8_t* /*s
       }
     }
     if (leader) trace_tile(p, lt, 5);
-    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
   }
 }
 
@@ -962,11 +962,15 @@ struct PairCfg {
   static constexpr int kBStagesRaw = kAvail / kBStage;
   static constexpr int kBStages = kBStagesRaw > 16 ? 16 : kBStagesRaw;
   static constexpr int kSmemBytes = 1024 + kAStages * kAStage + kBStages * kBStage + kAux;
-  static constexpr int kTmemCols = 2 * kAccCols;
+  // TMEM accumulator ring: as many buffers as the 512 columns hold (4 for N tiles up to 128 columns wide, 2 for 256).
+  // With two buffers the MMA warp idled ~15 % of a 64-channel tile waiting for the epilogue to hand one back (clock64
+  // traces); a deeper ring absorbs the epilogue's latency jitter.
+  static constexpr int kAccBufs = (4 * kAccCols <= 512) ? 4 : 2;
+  static constexpr int kTmemCols = kAccBufs * kAccCols;
   static_assert(BN == 64 || BN == 128 || BN == 256, "pair kernel: N tile 64, 128 or 256");
   static_assert(kTmemCols <= 512, "TMEM has 512 columns");
   static_assert(kBStages >= 3, "B ring too shallow");
-  static_assert(4 * BN * 4 + (2 * 16 + 2 * 2 + 8) * 8 <= kAux, "aux region too small");
+  static_assert(4 * BN * 4 + (2 * 16 + 3 * 4 + 8) * 8 <= kAux, "aux region too small");
 };
 
 template <int BN, int NL, int EW, bool STK = false>
@@ -984,9 +988,10 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) conv_pair_kernel(const __grid
   uint64_t* aempty_bar = afull_bar + Cfg::kAStages;         // [kAStages]
   uint64_t* bfull_bar = aempty_bar + Cfg::kAStages;         // [kBStages]  (used in the leader)
   uint64_t* bempty_bar = bfull_bar + Cfg::kBStages;         // [kBStages]
-  uint64_t* tfull_bar = bempty_bar + Cfg::kBStages;         // [2]
-  uint64_t* tempty_bar = tfull_bar + 2;                     // [2]        (used in the leader: 8 arrivals)
-  uint64_t* stg_bar = tempty_bar + 2;                       // [2] unused (layout shared with the other kernels)
+  constexpr int NACC = Cfg::kAccBufs;
+  uint64_t* tfull_bar = bempty_bar + Cfg::kBStages;         // [NACC]
+  uint64_t* tempty_bar = tfull_bar + NACC;                  // [NACC]     (used in the leader: 2*EW arrivals)
+  uint64_t* stg_bar = tempty_bar + NACC;                    // [2] unused (layout shared with the other kernels)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stg_bar + 2);
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
@@ -1000,11 +1005,11 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) conv_pair_kernel(const __grid
     ptx::prefetch_tmap(&p.w);
     for (int i = 0; i < Cfg::kAStages; ++i) { ptx::mbar_init(&afull_bar[i], 1); ptx::mbar_init(&aempty_bar[i], 1); }
     for (int i = 0; i < Cfg::kBStages; ++i) { ptx::mbar_init(&bfull_bar[i], 1); ptx::mbar_init(&bempty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NACC; ++i) {
       ptx::mbar_init(&tfull_bar[i], 1);
       ptx::mbar_init(&tempty_bar[i], 2 * EW);  // the epilogue warps of both CTAs of the pair
-      ptx::mbar_init(&stg_bar[i], 1);
     }
+    for (int i = 0; i < 2; ++i) ptx::mbar_init(&stg_bar[i], 1);
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
@@ -1166,11 +1171,11 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) conv_pair_kernel(const __grid
           if (++ia == Cfg::kAStages) { ia = 0; pha ^= 1; }
         }
         if (lane == 0) trace_tile(p, lt, 2);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else {
-    epilogue_warps<BN, NL, false, 0, STK, true, EW>(p, aux, s_scale, s_shift, tfull_bar, tempty_bar, stg_bar, tmem_base, warp, lane);
+    epilogue_warps<BN, NL, false, 0, STK, true, EW, NACC>(p, aux, s_scale, s_shift, tfull_bar, tempty_bar, stg_bar, tmem_base, warp, lane);
   }
 
   ptx::tc_fence_before();

@@ -482,7 +482,18 @@ Geo layer_geo(const lspg_ctx* h, const Layer& L, int B, int H, int W) {
     // a pair tile runs the tensor pipe at full rate while the N=64 single-CTA tile is shared-memory bound at ~60 %,
     // so the pair kernel already wins when its tiles fill about two thirds of the SMs
     const int enough = sms * 2 / 3;
-    if (L.cout_pad % 256 == 0 && g.m_tiles * (L.cout_pad / 256) * L.n_phases >= sms) bnp = 256;
+    // Tiles are equal-sized and statically strided over sms/2 clusters, so a launch costs ceil(pairs / clusters) waves of
+    // one tile each: 256 pairs of N=256 tiles on 74 clusters are 4 waves (3.46 needed), the same work as 512 pairs of N=128
+    // tiles is 7 half-sized waves (-12.5 %).  Take the N tile with the lower wave cost; ties go to the wider tile (fewer
+    // A operand reads).
+    static const bool no_wave_rule = getenv("LSPG_NO_WAVE_RULE") != nullptr;
+    auto wave_cost = [&](int bn) {
+      const long long pairs = static_cast<long long>(g.m_tiles) * (L.cout_pad / bn) * L.n_phases / 2;
+      const long long clusters = sms / 2;
+      return (pairs + clusters - 1) / clusters * bn;
+    };
+    if (L.cout_pad % 256 == 0 && g.m_tiles * (L.cout_pad / 256) * L.n_phases >= sms)
+      bnp = (!no_wave_rule && wave_cost(128) < wave_cost(256)) ? 128 : 256;
     else if (L.cout_pad % 128 == 0 && g.m_tiles * (L.cout_pad / 128) * L.n_phases >= enough) bnp = 128;
     else if (L.cout_pad == 64 && g.m_tiles * L.n_phases >= enough) bnp = 64;
     if (bnp) { g.pair = true; g.bn = bnp; }
