@@ -295,10 +295,21 @@ def main():
             f *= 4.0 / 9.0 if r["kind"] == 3 else 1.0
         exec_flops += f * (3.0 if args.mode == "parity" else 1.0)
     top = sorted(groups.items(), key=lambda kv: -kv[1]["ms"])[:6]
+    # dram__bytes_read.sum + dram__bytes_write.sum of the top kernel, per launch, from the committed ncu --set full capture of
+    # this workload (profiles/ncu_traffic.json names the report it was read from); ncu cannot run inside the timed region
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            cand_t = [t for t in json.load(open(tpath)) if t.get("batch") == B and t.get("mode") == args.mode and t.get("variant") == VARIANT]
+            traffic = cand_t[0] if cand_t else None
+        except Exception:
+            traffic = None
     roofline = {
-        "bound": "tensor", "kernel": "lspg::conv_umma_kernel (all conv launches of one step)",
+        "bound": "tensor", "kernel": "lspg::conv_pair_kernel / conv_umma_kernel / conv_patch_kernel (all conv launches of one step)",
         "achieved": achieved, "peak": tflops_peak, "unit": "TFLOP/s", "frac": achieved / tflops_peak, "peak_source": peak_src,
-        "traffic": None,
+        "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
+        "traffic_detail": traffic,
         "algorithmic_flops_per_step": flops_step, "kernel_ms_per_step": conv_ms_timed,
         "kernel_ms_per_step_event_pass": tot_ms, "pack_input_ms": prof_ms[0], "forwards_profiled": prof_n,
         "executed_tflops": exec_flops / (conv_ms_timed / 1e3) / 1e12 if conv_ms_timed > 0 else None,

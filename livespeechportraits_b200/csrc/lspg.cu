@@ -467,7 +467,7 @@ Geo layer_geo(const lspg_ctx* h, const Layer& L, int B, int H, int W) {
   g.m_tiles = (g.ws / g.tw) * (g.hs / g.th) * ((B + g.nb - 1) / g.nb);
   const int chunks = L.cin[0] / 64 + (L.n_src == 2 ? L.cin[1] / 64 : 0);
   g.k_items = g.patch ? chunks : chunks * L.n_taps;
-  static const bool small_bn128 = getenv("LSPG_SMALL_BN128") != nullptr;
+  static const bool small_bn128 = getenv("LSPG_NO_SMALL_BN128") == nullptr;
   if (L.kind == K_TAIL) g.bn = 16;
   else g.bn = (L.cout_pad % 128 == 0 && g.m_tiles * (L.cout_pad / 128) * L.n_phases >= h->num_sms_or_default()) ? 128 : 64;
   // per-tap kernel below 16^2: the N=128 tile halves the A traffic per MAC (the kernel is shared-memory bound) and split-K
@@ -504,7 +504,7 @@ Geo layer_geo(const lspg_ctx* h, const Layer& L, int B, int H, int W) {
   const int sms = h->num_sms_or_default();
   if (!no_split && !g.pair && L.kind != K_TAIL && g.tiles_per_split * 2 <= sms) {
     const int min_len = g.patch ? 1 : 4;                       // at least 4 K blocks (v1) / 1 chunk of all taps per split
-    static const bool split_floor = getenv("LSPG_SPLIT_FLOOR") != nullptr;
+    static const bool split_floor = getenv("LSPG_NO_SPLIT_FLOOR") == nullptr;
     int want = split_floor ? sms / g.tiles_per_split : (sms + g.tiles_per_split - 1) / g.tiles_per_split;   // floor: one wave
     int max_split = g.k_items / min_len;
     if (max_split < 1) max_split = 1;
