@@ -255,6 +255,7 @@ def main():
     barrier()
     t_wall1 = time.time()
     ms_total = e0.elapsed_time(e1)
+    launches = net.launches_per_forward()       # pack + convs + split-K finishers of the plan that was just timed
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     # Per-launch breakdown: the same K steps again with a CUDA event after every kernel.  Recording events forces
     # plain stream launches (no CUDA-graph replay, no PDL overlap), so this pass is a little slower than the timed
