@@ -156,12 +156,25 @@ def run_reference(args, rank: int):
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
+
+
+_REAL_STDOUT = None
+
+
+def emit(text: str) -> None:
+    """The ONE line of the contract, written to the process's original stdout."""
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (text + "\n").encode())
 
 
 def main():
-    global VARIANT, METRIC
+    global VARIANT, METRIC, _REAL_STDOUT
     args = parse()
+    # Libraries chat on stdout (NCCL prints its version line there): keep the original stdout for the JSON line only and
+    # send everything else that writes to fd 1 to stderr.
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     VARIANT = args.variant
     METRIC = f"512x512 frames/sec (Feature2Face_G {VARIANT} / {'May.yaml' if VARIANT == 'large' else 'Obama1.yaml'})"
     rank = int(os.environ.get("RANK", "0"))
@@ -427,7 +440,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu,
         }
         line.update(extras)
-        print(json.dumps(line), flush=True)
+        emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
