@@ -117,6 +117,10 @@ typedef struct lspg_layer_info {
   char bn_key[96];          /* "" when the conv has no BatchNorm */
 } lspg_layer_info;
 
+/* Test hook (host only, no device): q = n / d computed exactly as the kernels' tile decode does it (multiply-high by a
+ * launch-time constant, csrc/conv_umma.cuh make_fast_div / fast_div); valid for n < 2^31, d >= 1. */
+int lspg_debug_fast_div(uint32_t n, uint32_t d, uint32_t* q);
+
 int lspg_num_layers(lspg_handle h, int* out);
 int lspg_layer_info_get(lspg_handle h, int layer, lspg_layer_info* out);
 /* Packed weights as the kernels see them: bf16 bit patterns, limb 0 = hi, limb 1 = lo (w - hi);

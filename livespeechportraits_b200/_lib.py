@@ -15,7 +15,7 @@ SYMBOLS = [
     "lspg_last_error",
     "lspg_num_layers", "lspg_layer_info_get", "lspg_layer_packed", "lspg_layer_affine", "lspg_num_tensors",
     "lspg_tensor_shape", "lspg_debug_read_tensor", "lspg_launches_per_forward", "lspg_flops_per_frame",
-    "lspg_profile_enable", "lspg_profile_read", "lspg_debug_read_trace",
+    "lspg_profile_enable", "lspg_profile_read", "lspg_debug_read_trace", "lspg_debug_fast_div",
 ]
 
 
@@ -70,6 +70,7 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     lib.lspg_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int,
                                  C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
     lib.lspg_forward_image.argtypes = lib.lspg_forward.argtypes
+    lib.lspg_debug_fast_div.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]
     lib.lspg_draw_feature_maps.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                            C.c_void_p]
     lib.lspg_destroy.argtypes = [C.c_void_p]

@@ -1233,6 +1233,14 @@ int lspg_debug_read_tensor(lspg_handle h, int id, int limb, uint16_t* dst, int64
   return LSPG_OK;
 }
 
+int lspg_debug_fast_div(uint32_t n, uint32_t d, uint32_t* q) {
+  if (!q || d == 0 || n >= (1u << 31)) return fail(LSPG_EINVAL, "fast_div: need q, d >= 1 and n < 2^31");
+  const FastDiv f = make_fast_div(d);
+  // host form of the device's __umulhi(n, mul) >> shr
+  *q = (f.d == 1) ? n : static_cast<uint32_t>((static_cast<uint64_t>(n) * f.mul) >> 32) >> f.shr;
+  return LSPG_OK;
+}
+
 int lspg_debug_read_trace(lspg_handle h, uint64_t* dst, int64_t count) {
   if (!h || !dst) return fail(LSPG_EINVAL, "null argument");
   if (!h->trace_buf) return fail(LSPG_ESTATE, "no trace recorded (set LSPG_TRACE_LAYER=<layer index> before the first forward)");

@@ -179,3 +179,21 @@ def test_drop_in_through_the_reference_model_class(tmp_path):
             model.inference(torch.zeros(1, 1, 256, 256), torch.zeros(1, 12, 256, 256))
     finally:
         ref_mod.Feature2Face_G = original
+
+
+def test_tile_decode_division_by_multiply_high_is_exact():
+    """decode_tile divides tile indices by launch-time constants with multiply-high + shift (csrc/conv_umma.cuh fast_div)."""
+    import random
+    lib = _lib.load()
+    rng = random.Random(0)
+    q = C.c_uint32()
+    divisors = list(range(1, 300)) + [2 ** k for k in range(1, 31)] + [2 ** k - 1 for k in range(2, 31)] + \
+        [2 ** k + 1 for k in range(1, 30)] + [37, 74, 148, 8192, 9472, 65535, 65537, 2 ** 31 - 1] + [rng.randrange(1, 2 ** 31) for _ in range(300)]
+    for d in divisors:
+        ns = [0, 1, d - 1, d, d + 1, 2 * d - 1, 2 * d, 2 ** 31 - 1, 2 ** 31 - d] + [rng.randrange(0, 2 ** 31) for _ in range(40)]
+        for n in ns:
+            if 0 <= n < 2 ** 31:
+                assert lib.lspg_debug_fast_div(n, d, C.byref(q)) == 0
+                assert q.value == n // d, (n, d, q.value)
+    assert lib.lspg_debug_fast_div(5, 0, C.byref(q)) == -1
+    assert lib.lspg_debug_fast_div(2 ** 31, 3, C.byref(q)) == -1
