@@ -1033,6 +1033,7 @@ int lspg_load_weights(lspg_handle h, const lspg_tensor* tensors, int n) {
     *changed = true;
     return LSPG_OK;
   };
+  bool synced = false;
   for (auto& L : h->layers) {
     const int cin_total = (L.kind == K_HEAD) ? h->in_nc : (L.cin[0] + (L.n_src == 2 ? L.cin[1] : 0));
     const size_t wn = static_cast<size_t>(L.cout) * cin_total * 9;
@@ -1049,6 +1050,9 @@ int lspg_load_weights(lspg_handle h, const lspg_tensor* tensors, int n) {
     }
     if (changed || L.dirty) {
       pack_layer(h, L);
+      // Packed weights are updated in place (cached plans and graphs keep pointing at them): a forward that is still
+      // running on any stream must not see half-written tiles.  Loading weights is rare; one device-wide sync is cheap.
+      if (h->device >= 0 && !synced) { CUDA_TRY(cudaDeviceSynchronize()); synced = true; }
       if ((rc = upload_layer(h, L))) return rc;
       L.dirty = false;
     }
