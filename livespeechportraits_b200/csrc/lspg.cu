@@ -1008,6 +1008,7 @@ int lspg_destroy(lspg_handle h) {
     for (auto& kv : h->plans)
       for (auto& ge : kv.second->graphs) cudaGraphExecDestroy(ge.exec);
     if (h->capture_stream) cudaStreamDestroy(h->capture_stream);
+    if (h->trace_buf) cudaFree(h->trace_buf);
   }
   delete h;
   return LSPG_OK;
