@@ -117,6 +117,19 @@ typedef struct lspg_layer_info {
   char bn_key[96];          /* "" when the conv has no BatchNorm */
 } lspg_layer_info;
 
+/* Tiling / kernel choice of one layer for a problem size, as the launch plan will make it (host logic only; works on a
+ * host-only handle, where the SM count defaults to 148).  Lets the CPU tests pin the planner. */
+typedef struct lspg_layer_geo {
+  int kernel;            /* 0 conv_umma_kernel (one box per tap), 1 conv_patch_kernel, 2 conv_pair_kernel (cta_group::2) */
+  int bn;                /* N tile */
+  int tile_w, tile_h, tile_n;   /* output tile = tile_w x tile_h pixels x tile_n images = 128 rows */
+  int m_tiles, n_tiles, n_phases;
+  int n_split, split_len, k_items;   /* split-K: K loop of k_items cut into n_split ranges of split_len */
+  int ctas;              /* CTAs launched = min(tiles * n_split, SMs), even for the pair kernel */
+  int64_t partial_bytes; /* fp32 split-K partials this layer needs in the scratch region */
+} lspg_layer_geo;
+int lspg_debug_layer_geo(lspg_handle h, int layer, int batch, int height, int width, lspg_layer_geo* out);
+
 /* Test hook (host only, no device): q = n / d computed exactly as the kernels' tile decode does it (multiply-high by a
  * launch-time constant, csrc/conv_umma.cuh make_fast_div / fast_div); valid for n < 2^31, d >= 1. */
 int lspg_debug_fast_div(uint32_t n, uint32_t d, uint32_t* q);

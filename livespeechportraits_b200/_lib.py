@@ -15,7 +15,7 @@ SYMBOLS = [
     "lspg_last_error",
     "lspg_num_layers", "lspg_layer_info_get", "lspg_layer_packed", "lspg_layer_affine", "lspg_num_tensors",
     "lspg_tensor_shape", "lspg_debug_read_tensor", "lspg_launches_per_forward", "lspg_flops_per_frame",
-    "lspg_profile_enable", "lspg_profile_read", "lspg_debug_read_trace", "lspg_debug_fast_div",
+    "lspg_profile_enable", "lspg_profile_read", "lspg_debug_read_trace", "lspg_debug_fast_div", "lspg_debug_layer_geo",
 ]
 
 
@@ -31,6 +31,12 @@ class LspgLayerInfo(C.Structure):
         ("tap_map", (C.c_int8 * 9) * 4), ("tap_dx", (C.c_int8 * 9) * 4), ("tap_dy", (C.c_int8 * 9) * 4),
         ("conv_key", C.c_char * 96), ("bn_key", C.c_char * 96),
     ]
+
+
+class LspgLayerGeo(C.Structure):
+    _fields_ = [("kernel", C.c_int), ("bn", C.c_int), ("tile_w", C.c_int), ("tile_h", C.c_int), ("tile_n", C.c_int),
+                ("m_tiles", C.c_int), ("n_tiles", C.c_int), ("n_phases", C.c_int), ("n_split", C.c_int), ("split_len", C.c_int),
+                ("k_items", C.c_int), ("ctas", C.c_int), ("partial_bytes", C.c_int64)]
 
 
 class LspgError(RuntimeError):
@@ -70,6 +76,7 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     lib.lspg_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int,
                                  C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
     lib.lspg_forward_image.argtypes = lib.lspg_forward.argtypes
+    lib.lspg_debug_layer_geo.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(LspgLayerGeo)]
     lib.lspg_debug_fast_div.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]
     lib.lspg_draw_feature_maps.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                            C.c_void_p]

@@ -1238,6 +1238,27 @@ int lspg_debug_read_tensor(lspg_handle h, int id, int limb, uint16_t* dst, int64
   return LSPG_OK;
 }
 
+int lspg_debug_layer_geo(lspg_handle h, int layer, int batch, int height, int width, lspg_layer_geo* o) {
+  if (!h || !o) return fail(LSPG_EINVAL, "null argument");
+  if (layer < 0 || layer >= static_cast<int>(h->layers.size())) return fail(LSPG_EINVAL, "layer %d out of range", layer);
+  int rc = check_shape(h, batch, height, width, LSPG_MODE_PARITY);
+  if (rc) return rc;
+  const Layer& L = h->layers[layer];
+  const Geo g = layer_geo(h, L, batch, height, width);
+  memset(o, 0, sizeof(*o));
+  o->kernel = g.pair ? 2 : (g.patch ? 1 : 0);
+  o->bn = g.bn;
+  o->tile_w = g.tw; o->tile_h = g.th; o->tile_n = g.nb;
+  o->m_tiles = g.m_tiles; o->n_tiles = g.n_tiles; o->n_phases = L.n_phases;
+  o->n_split = g.n_split; o->split_len = g.split_len; o->k_items = g.k_items;
+  const int sms = h->num_sms_or_default();
+  int ctas = std::min(g.tiles_per_split * g.n_split, sms);
+  if (g.pair) ctas -= ctas % 2;
+  o->ctas = ctas;
+  o->partial_bytes = static_cast<int64_t>(g.partial_bytes);
+  return LSPG_OK;
+}
+
 int lspg_debug_fast_div(uint32_t n, uint32_t d, uint32_t* q) {
   if (!q || d == 0 || n >= (1u << 31)) return fail(LSPG_EINVAL, "fast_div: need q, d >= 1 and n < 2^31");
   const FastDiv f = make_fast_div(d);

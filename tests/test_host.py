@@ -197,3 +197,60 @@ def test_tile_decode_division_by_multiply_high_is_exact():
                 assert q.value == n // d, (n, d, q.value)
     assert lib.lspg_debug_fast_div(5, 0, C.byref(q)) == -1
     assert lib.lspg_debug_fast_div(2 ** 31, 3, C.byref(q)) == -1
+
+
+def _geo_table(variant, batch, height=512, width=512):
+    lib = _lib.load()
+    h = C.c_void_p()
+    assert lib.lspg_create(C.byref(h), _lib.LSPG_VARIANT[variant], 64, 8, 13, 3, -1) == 0
+    n = C.c_int()
+    assert lib.lspg_num_layers(h, C.byref(n)) == 0
+    out = []
+    for i in range(n.value):
+        g = _lib.LspgLayerGeo()
+        assert lib.lspg_debug_layer_geo(h, i, batch, height, width, C.byref(g)) == 0
+        info = _lib.LspgLayerInfo()
+        assert lib.lspg_layer_info_get(h, i, C.byref(info)) == 0
+        out.append((info, g))
+    need = C.c_size_t()
+    assert lib.lspg_workspace_bytes(h, batch, height, width, 1, C.byref(need)) == 0
+    lib.lspg_destroy(h)
+    return out, need.value
+
+
+@pytest.mark.parametrize("variant,batch", [("large", 1), ("large", 16), ("large", 32), ("large", 37), ("normal", 5), ("normal", 32)])
+def test_planner_invariants(variant, batch):
+    """The launch planner (layer_geo in csrc/lspg.cu) on the host: tile shapes, kernel choice, split-K and wave rules."""
+    table, ws = _geo_table(variant, batch)
+    sms = 148
+    for info, g in table:
+        assert g.tile_w * g.tile_h * g.tile_n == 128                       # one UMMA M tile
+        assert g.bn in (16, 64, 128, 256) and info.cout_pad % g.bn == 0 and g.n_tiles == info.cout_pad // g.bn
+        tiles = g.m_tiles * g.n_tiles * g.n_phases
+        if g.kernel == 2:                                                    # cta_group::2: pairs of neighbouring M tiles
+            assert g.m_tiles % 2 == 0 and g.n_split == 1 and g.ctas % 2 == 0 and (g.tile_w, g.tile_h) == (8, 16)
+        if g.kernel in (1, 2):
+            assert info.kind != 2                                            # stride-2 convs use the per-tap kernel
+        if g.n_split > 1:
+            assert g.kernel != 2
+            assert tiles * g.n_split <= sms                                  # split-K never spills into a second wave
+            assert (g.n_split - 1) * g.split_len < g.k_items <= g.n_split * g.split_len   # every split has work
+            assert g.partial_bytes == g.n_split * tiles * 128 * g.bn * 4
+        else:
+            assert g.partial_bytes == 0
+        assert 1 <= g.ctas <= sms
+    assert ws > max(g.partial_bytes for _, g in table)
+
+
+def test_planner_picks_the_n_tile_with_fewer_waves():
+    def bn_of(batch, cout, hw):
+        table, _ = _geo_table("large", batch)
+        return {g.bn for info, g in table if info.kind == 1 and info.cout == cout and g.kernel == 2
+                and g.m_tiles == batch * (hw // 8) * (hw // 16)}
+    # 256 -> 256 @64^2, 16 frames: 256 pairs of N=256 tiles = 4 waves of 74 clusters; 512 pairs of N=128 = 7 half-size waves
+    assert bn_of(16, 256, 64) == {128}
+    assert bn_of(32, 256, 64) == {256}        # 7 waves vs 14 half-size waves: tie -> the wider tile
+    assert bn_of(16, 512, 32) == {256}        # 2 vs 4 half-size: tie
+    assert bn_of(32, 512, 32) == {128}        # 4 vs 7 half-size
+    # the 64-channel layers always take the resident-weights N=64 pair kernel
+    assert bn_of(16, 64, 256) == {64}
