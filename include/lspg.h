@@ -74,7 +74,11 @@ int lspg_workspace_bytes(lspg_handle h, int batch, int height, int width, int mo
  *                every frame, as demo.py:266 does)
  *   out:         device fp32 [B,3,H,W] contiguous, values in (-1,1)
  * A single [B,13,H,W] tensor x is passed as feature_map=x, cand=x+H*W, both strides 13*H*W.
- * H and W must be multiples of 256 (8 stride-2 stages).  Asynchronous on `stream` (a cudaStream_t). */
+ * H and W must be powers of two >= 256 (8 stride-2 stages; every level must tile into the kernels' power-of-two boxes -
+ * the reference accepts any multiple of 256, e.g. 768, which this library rejects with LSPG_EINVAL rather than
+ * mis-render).  Asynchronous on `stream` (a cudaStream_t).  The launches of one (B,H,W,mode,workspace) plan are captured
+ * once as a CUDA graph; a call with different feature_map / cand / out pointers patches two kernel nodes in place
+ * (cudaGraphExecKernelNodeSetParams), it does not re-capture.  Returns LSPG_ESTATE if any conv weight was never loaded. */
 int lspg_forward(lspg_handle h, const float* feature_map, int64_t fm_bstride, const float* cand,
                  int64_t cand_bstride, float* out, int batch, int height, int width, void* workspace,
                  size_t workspace_bytes, int mode, void* stream);
@@ -97,6 +101,10 @@ int lspg_forward_image(lspg_handle h, const float* feature_map, int64_t fm_bstri
  * Asynchronous on `stream`. */
 int lspg_draw_feature_maps(lspg_handle h, const float* landmarks, const float* shoulders, int n_shoulder_points,
                            float* out_fm, int batch, int height, int width, void* stream);
+
+/* Tell the library that the caller is about to free (or reuse) `workspace`: waits for the device, then drops every cached
+ * plan / CUDA graph that points into it.  workspace == NULL drops all plans.  Replaces nothing in the reference. */
+int lspg_release_workspace(lspg_handle h, void* workspace);
 
 /* Replaces nothing in the reference (module garbage collection). */
 int lspg_destroy(lspg_handle h);
@@ -148,6 +156,9 @@ int lspg_debug_read_tensor(lspg_handle h, int id, int limb, uint16_t* dst, int64
 /* Debug: with LSPG_TRACE_LAYER=<i> in the environment the conv kernel of layer i stamps clock64() at its pipeline
  * milestones (conv_umma.cuh: kTraceSlots values per CTA, 256 CTAs); this copies them out. */
 int lspg_debug_read_trace(lspg_handle h, uint64_t* dst, int64_t count);
+/* CUDA-graph bookkeeping since lspg_create: graphs captured + instantiated, in-place I/O pointer updates, and re-captures
+ * forced by a failed update (expected 0). */
+int lspg_graph_stats(lspg_handle h, int64_t* captures, int64_t* io_updates, int64_t* recaptures);
 /* Kernels one lspg_forward call launches (for bench.py's gpu_launches accounting). */
 int lspg_launches_per_forward(lspg_handle h, int* out);
 /* Per-launch timing: when enabled, every lspg_forward records a CUDA event on `stream` before its first

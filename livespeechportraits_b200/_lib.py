@@ -16,6 +16,7 @@ SYMBOLS = [
     "lspg_num_layers", "lspg_layer_info_get", "lspg_layer_packed", "lspg_layer_affine", "lspg_num_tensors",
     "lspg_tensor_shape", "lspg_debug_read_tensor", "lspg_launches_per_forward", "lspg_flops_per_frame",
     "lspg_profile_enable", "lspg_profile_read", "lspg_debug_read_trace", "lspg_debug_fast_div", "lspg_debug_layer_geo",
+    "lspg_graph_stats", "lspg_release_workspace",
 ]
 
 
@@ -65,9 +66,13 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     if build_if_missing and _build.needs_build():
         try:
             _build.build_library()
-        except Exception:
+        except Exception as exc:
             if not os.path.exists(path):
                 raise
+            # a stale library next to newer sources: usable (the GPU box has no reason to rebuild), but say so loudly
+            import warnings
+            warnings.warn(f"liblspg.so is older than its sources and could not be rebuilt ({exc}); using the existing binary",
+                          RuntimeWarning)
     lib = C.CDLL(path)
     lib.lspg_last_error.restype = C.c_char_p
     lib.lspg_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
@@ -81,6 +86,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     lib.lspg_draw_feature_maps.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                            C.c_void_p]
     lib.lspg_destroy.argtypes = [C.c_void_p]
+    lib.lspg_release_workspace.argtypes = [C.c_void_p, C.c_void_p]
+    lib.lspg_graph_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     lib.lspg_num_layers.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
     lib.lspg_layer_info_get.argtypes = [C.c_void_p, C.c_int, C.POINTER(LspgLayerInfo)]
     lib.lspg_layer_packed.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64]

@@ -13,15 +13,17 @@
 //     stored through four phase views of the output, and torch.cat([skip, deeper]) is two K ranges fed from
 //     two tensor maps - so upsample, concat, padding and stride never touch HBM as separate passes.
 //   * B tiles come from a packed weight tensor [phase*limb][Cout][K] (K-major), same 128B-swizzled layout.
-//   * Accumulators live in TMEM (double buffered, 2 x BN columns); the epilogue reads them with
-//     tcgen05.ld, applies the folded eval-BatchNorm scale/shift in fp32, adds the residual tile (TMA-loaded
-//     into the same staging buffer the result is written back to), ReLU, converts to bf16 and hands the
-//     tile to a TMA store.  The tail variant applies tanh and scatters fp32 NCHW directly.
+//   * Accumulators live in a TMEM ring (2-4 buffers); the epilogue warps read them with tcgen05.ld, apply the folded
+//     eval-BatchNorm scale/shift in fp32, add the residual (256-bit ld.global.nc straight from the NHWC tensor, requested
+//     one piece ahead), ReLU, convert to bf16 (hi, lo) and write the NHWC output with 256-bit global stores (no smem
+//     staging, no TMA store).  The tail variant applies tanh and scatters fp32 NCHW or uint8 HWC directly.
 //   * NL = 2 ("parity" precision): activations and weights are split bf16 hi + lo limbs; each K step issues
 //     hi*hi + hi*lo + lo*hi (~16 mantissa bits, fp32 accumulate) and the epilogue writes both limbs.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..5 = epilogue
-// (TMEM lane quarter = warp_id % 4).  Persistent: each CTA walks tiles blockIdx.x, +gridDim.x, ...
+// Three kernels share the epilogue: conv_umma_kernel (one TMA box per tap; stride-2 convs and everything below 16x16;
+// 192 threads = producer warp + MMA warp + 4 epilogue warps), conv_patch_kernel (one halo patch per chunk; head and tail)
+// and conv_pair_kernel (cta_group::2 over a 2-CTA cluster; the wide layers; 320 threads = 2 role warps + 8 epilogue
+// warps).  All are persistent: each CTA walks tiles blockIdx.x, +gridDim.x, ...
 #pragma once
 #include <cuda_bf16.h>
 #include "ptx.cuh"
@@ -74,7 +76,6 @@ struct alignas(64) ConvParams {
   float* out_f32;            // tail only: fp32 NCHW [B, 3, 2*hs, 2*ws]
   uint8_t* out_u8;           // tail only, optional: uint8 HWC image [B, 2*hs, 2*ws, 3] = util.tensor2im fused (then out_f32 is unused)
   float* partial;            // split-K partial tiles (see n_split)
-  int* split_counter;        // [tiles_per_split] arrival counters (zero between forwards); null = two-pass (finisher kernel)
   unsigned long long* trace; // debug: per-CTA clock64 stamps (null in production), see kTraceSlots
   int32_t out_channels, res_channels;
   int32_t out_up;            // the sampling grid is the source of a folded x2 upsample (phase tc.z -> (2y+py, 2x+px))
@@ -218,7 +219,6 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, uint8_t* /*s
   static_assert(!(TAIL && EW != 4), "the tail epilogue uses 4 warps");
   constexpr int kEpi = EW * 32;
   constexpr int kGroups = EW / 4;
-  int* fix_flag = reinterpret_cast<int*>(stg_bar + 2) + 1;   // smem word right after the TMEM-address slot
   ptx::pdl_wait();   // residual reads, output / split-K partial writes must not overtake the previous kernel
   const int q = warp & 3;                     // TMEM lane quarter this warp may read
   const int grp = (warp - 2) >> 2;            // which interleaved share of the 32-column pieces this warp takes
@@ -261,8 +261,7 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, uint8_t* /*s
   // Residual of this thread's pixel: 32 channels x NL limbs per 32-column piece, always requested one piece ahead - the
   // first piece of a tile while the previous tile is being finished - so that its L2/HBM latency never sits between the
   // accumulator becoming ready and the TMEM buffer being handed back to the MMA warp.
-  constexpr int kPiecesR = (BN >= 32) ? BN / 32 : 1;
-  const bool use_res = !TAIL && p.has_res && (p.n_split == 1 || p.split_counter != nullptr);
+  const bool use_res = !TAIL && p.has_res && p.n_split == 1;
   uint4 rs[NL][4];
   auto load_res = [&](const TileCoord& c, int c32) {
     const int n = c.n0 + nb_, y = c.y0 + th_, x = c.x0 + tw_;
@@ -286,7 +285,6 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, uint8_t* /*s
     const TileCoord tc = tc_next;
     if (leader) trace_tile(p, lt, 3);
     const bool split_mode = !TAIL && p.n_split > 1;
-    bool fixup = false;
     if (tc.nt != cur_nt) fetch_affine(tc.nt);
     const int t_next = t + gridDim.x;
     if (t_next < p.total_tiles) tc_next = decode_tile(p, t_next);
@@ -372,53 +370,7 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, uint8_t* /*s
           for (int e = 0; e < 8; ++e)
             *reinterpret_cast<uint4*>(dst + c32 * 32 + e * 4) = make_uint4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
         }
-        if (p.split_counter != nullptr) {
-          // In-kernel finish (opt-in, LSPG_SPLITK_FIXUP): the CTA that publishes the LAST partial of an output tile sums
-          // all of them (in split order, so the result does not depend on which CTA that is) and runs the epilogue below.
-          __threadfence();
-          ptx::named_bar_sync(2, kEpi);
-          if (leader) {
-            const int tile_id = t - tc.split * p.tiles_per_split;
-            const int old = atomicAdd(p.split_counter + tile_id, 1);
-            const int last = (old == p.n_split - 1) ? 1 : 0;
-            if (last) p.split_counter[tile_id] = 0;          // ready for the next forward
-            *fix_flag = last;
-          }
-          ptx::named_bar_sync(3, kEpi);
-          fixup = (*fix_flag != 0);
-          __threadfence();
-          if (fixup) {
-            float* base = p.partial + static_cast<size_t>(t - tc.split * p.tiles_per_split) * kTileM * BN;
-            const size_t split_stride = static_cast<size_t>(p.tiles_per_split) * kTileM * BN;
-            auto ldcg = [](const float* qq) {
-              float4 a;
-              asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(qq));
-              return a;
-            };
-            for (int k = etid; k < kTileM * BN / 4; k += kEpi) {
-              float* qq = base + static_cast<size_t>(k) * 4;
-              float4 acc4 = ldcg(qq);
-              int sp = 1;
-              for (; sp + 4 <= p.n_split; sp += 4) {
-                const float4 a0 = ldcg(qq + (sp + 0) * split_stride), a1 = ldcg(qq + (sp + 1) * split_stride);
-                const float4 a2 = ldcg(qq + (sp + 2) * split_stride), a3 = ldcg(qq + (sp + 3) * split_stride);
-                acc4.x += a0.x; acc4.y += a0.y; acc4.z += a0.z; acc4.w += a0.w;
-                acc4.x += a1.x; acc4.y += a1.y; acc4.z += a1.z; acc4.w += a1.w;
-                acc4.x += a2.x; acc4.y += a2.y; acc4.z += a2.z; acc4.w += a2.w;
-                acc4.x += a3.x; acc4.y += a3.y; acc4.z += a3.z; acc4.w += a3.w;
-              }
-              for (; sp < p.n_split; ++sp) {
-                const float4 a0 = ldcg(qq + sp * split_stride);
-                acc4.x += a0.x; acc4.y += a0.y; acc4.z += a0.z; acc4.w += a0.w;
-              }
-              *reinterpret_cast<float4*>(qq) = acc4;
-            }
-            __threadfence();
-            ptx::named_bar_sync(2, kEpi);
-          }
-        }
-      }
-      if (!split_mode || fixup) {
+      } else {
         // ---- regular: scale/shift (+ residual) + ReLU, bf16 (hi, lo), written straight to the NHWC output.
         // Each thread owns one pixel row; per 32-column piece it reads its residual (64 B per limb) and writes its output
         // with 256-bit (one 32-byte sector) global accesses.  No smem staging and no TMA store: a TMA store queues behind
@@ -430,19 +382,7 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, uint8_t* /*s
 #pragma unroll 1
         for (int c32 = grp; c32 < kPieces; c32 += kGroups) {
           uint32_t vv[32];
-          if (fixup) {
-            // the summed tile was written back to split 0's slot by the cooperative pass above
-            const float* src0 = p.partial + (static_cast<size_t>(t - tc.split * p.tiles_per_split) * kTileM + row) * BN + c32 * 32;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              float4 a;
-              asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(src0 + e * 4));
-              vv[4 * e] = __float_as_uint(a.x);
-              vv[4 * e + 1] = __float_as_uint(a.y);
-              vv[4 * e + 2] = __float_as_uint(a.z);
-              vv[4 * e + 3] = __float_as_uint(a.w);
-            }
-          } else {
+          {
             ptx::tmem_ld_32x32(t_acc + c32 * 32, vv);
             if constexpr (STACK) {
               // second half of the stacked accumulator, 16 columns at a time (register pressure: 168 per thread at 10 warps)

@@ -86,6 +86,7 @@ struct Layer {
   std::vector<uint16_t> packed[2];           // [limb][phase][cout_pad][k_total]
   std::vector<float> scale, shift;           // [cout_pad]
   bool dirty = true;
+  bool has_w = false;                        // the conv weight has been supplied at least once (forward refuses otherwise)
   // device copies
   uint16_t* d_w = nullptr;                   // [limb][phase][cout_pad][k_total]
   float* d_scale = nullptr;
@@ -111,13 +112,16 @@ struct IoKey {
   }
 };
 
-struct GraphEntry {
-  IoKey io;
-  cudaGraphExec_t exec = nullptr;
-};
-
 struct Plan {
-  std::vector<GraphEntry> graphs;      // instantiated CUDA graphs of this plan, keyed by the I/O pointers
+  // ONE instantiated CUDA graph per plan.  The caller's pointers (feature maps, candidates, output) are parameters of
+  // two nodes only - the input packer and the tail conv - and are patched with cudaGraphExecKernelNodeSetParams when a
+  // call brings different ones, so a caller that holds its outputs never re-captures (see forward_impl).
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  cudaGraphNode_t pack_node = nullptr, tail_node = nullptr;
+  cudaKernelNodeParams pack_np{}, tail_np{};   // func / grid / block / smem of the two nodes as captured
+  IoKey io{};                                  // pointers currently baked into `exec`
+  unsigned long long last_use = 0;             // LRU stamp (lspg_ctx::use_clock)
   int batch = 0, height = 0, width = 0, mode = 0;
   void* workspace = nullptr;
   std::vector<size_t> tensor_off;            // byte offset of limb 0 of each activation tensor
@@ -142,6 +146,9 @@ struct lspg_ctx {
   Plan* last_plan = nullptr;
   int num_sms_or_default() const { return num_sms > 0 ? num_sms : 148; }
   cudaStream_t capture_stream = nullptr;
+  long long n_captures = 0, n_io_updates = 0, n_recaptures = 0;   // graph bookkeeping (lspg_graph_stats)
+  const void* tail_func = nullptr;           // host stub of the tail kernel the last enqueue launched
+  unsigned long long use_clock = 0;
   unsigned long long* trace_buf = nullptr;   // debug (LSPG_TRACE_LAYER): clock64 stamps of one layer's CTAs
   bool profiling = false;
   std::vector<std::vector<cudaEvent_t>> prof_events;   // one event set per recorded forward
@@ -425,10 +432,7 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 int nl_of(int mode) { return mode == LSPG_MODE_PARITY ? 2 : 1; }
 
 // conv_pair_kernel variant with stacked [B_hi; B_lo] operands (parity mode, N tile 64); see PairCfg
-bool pair_stacked(int bn, int NL) {
-  static const bool off = getenv("LSPG_NO_PAIR_STACK") != nullptr;
-  return !off && bn == 64 && NL == 2;
-}
+bool pair_stacked(int bn, int NL) { return bn == 64 && NL == 2; }
 
 size_t tensor_bytes_one_limb(const TensorInfo& t, int B, int H, int W) {
   return static_cast<size_t>(B) * (H >> t.shift) * (W >> t.shift) * t.channels * 2;
@@ -467,12 +471,11 @@ Geo layer_geo(const lspg_ctx* h, const Layer& L, int B, int H, int W) {
   g.m_tiles = (g.ws / g.tw) * (g.hs / g.th) * ((B + g.nb - 1) / g.nb);
   const int chunks = L.cin[0] / 64 + (L.n_src == 2 ? L.cin[1] / 64 : 0);
   g.k_items = g.patch ? chunks : chunks * L.n_taps;
-  static const bool small_bn128 = getenv("LSPG_NO_SMALL_BN128") == nullptr;
   if (L.kind == K_TAIL) g.bn = 16;
   else g.bn = (L.cout_pad % 128 == 0 && g.m_tiles * (L.cout_pad / 128) * L.n_phases >= h->num_sms_or_default()) ? 128 : 64;
   // per-tap kernel below 16^2: the N=128 tile halves the A traffic per MAC (the kernel is shared-memory bound) and split-K
   // restores the CTA count
-  if (small_bn128 && !g.patch && L.kind != K_TAIL && L.cout_pad % 128 == 0 && g.m_tiles >= 8) g.bn = 128;
+  if (!g.patch && L.kind != K_TAIL && L.cout_pad % 128 == 0 && g.m_tiles >= 8) g.bn = 128;
   // CTA-pair kernel for the wide layers: N tile 256 (or 128), two neighbouring M tiles per cluster
   static const bool no_pair = getenv("LSPG_NO_PAIR") != nullptr;
   g.pair = false;
@@ -486,14 +489,13 @@ Geo layer_geo(const lspg_ctx* h, const Layer& L, int B, int H, int W) {
     // one tile each: 256 pairs of N=256 tiles on 74 clusters are 4 waves (3.46 needed), the same work as 512 pairs of N=128
     // tiles is 7 half-sized waves (-12.5 %).  Take the N tile with the lower wave cost; ties go to the wider tile (fewer
     // A operand reads).
-    static const bool no_wave_rule = getenv("LSPG_NO_WAVE_RULE") != nullptr;
     auto wave_cost = [&](int bn) {
       const long long pairs = static_cast<long long>(g.m_tiles) * (L.cout_pad / bn) * L.n_phases / 2;
       const long long clusters = sms / 2;
       return (pairs + clusters - 1) / clusters * bn;
     };
     if (L.cout_pad % 256 == 0 && g.m_tiles * (L.cout_pad / 256) * L.n_phases >= sms)
-      bnp = (!no_wave_rule && wave_cost(128) < wave_cost(256)) ? 128 : 256;
+      bnp = wave_cost(128) < wave_cost(256) ? 128 : 256;
     else if (L.cout_pad % 128 == 0 && g.m_tiles * (L.cout_pad / 128) * L.n_phases >= enough) bnp = 128;
     else if (L.cout_pad == 64 && g.m_tiles * L.n_phases >= enough) bnp = 64;
     if (bnp) { g.pair = true; g.bn = bnp; }
@@ -504,8 +506,7 @@ Geo layer_geo(const lspg_ctx* h, const Layer& L, int B, int H, int W) {
   const int sms = h->num_sms_or_default();
   if (!no_split && !g.pair && L.kind != K_TAIL && g.tiles_per_split * 2 <= sms) {
     const int min_len = g.patch ? 1 : 4;                       // at least 4 K blocks (v1) / 1 chunk of all taps per split
-    static const bool split_floor = getenv("LSPG_NO_SPLIT_FLOOR") == nullptr;
-    int want = split_floor ? sms / g.tiles_per_split : (sms + g.tiles_per_split - 1) / g.tiles_per_split;   // floor: one wave
+    int want = sms / g.tiles_per_split;                        // floor: tiles x splits stay within one wave
     int max_split = g.k_items / min_len;
     if (max_split < 1) max_split = 1;
     if (want > max_split) want = max_split;
@@ -519,12 +520,10 @@ Geo layer_geo(const lspg_ctx* h, const Layer& L, int B, int H, int W) {
   return g;
 }
 
-constexpr size_t kCounterBytes = 4096;     // split-K arrival counters (one int per output tile of the layer in flight)
-
 size_t scratch_bytes(const lspg_ctx* h, int B, int H, int W) {
   size_t m = 0;
   for (const auto& L : h->layers) m = std::max(m, layer_geo(h, L, B, H, W).partial_bytes);
-  return kCounterBytes + align_up(m, 1024);
+  return align_up(m, 1024);
 }
 
 size_t workspace_bytes(const lspg_ctx* h, int B, int H, int W, int mode) {
@@ -539,6 +538,16 @@ int check_shape(const lspg_ctx* h, int B, int H, int W, int mode) {
   if (H < m || W < m || H % m || W % m)
     return fail(LSPG_EINVAL, "height/width must be positive multiples of %d (got %dx%d)", m, H, W);
   if (mode != LSPG_MODE_FAST && mode != LSPG_MODE_PARITY) return fail(LSPG_EINVAL, "unknown precision mode %d", mode);
+  // Every level of the U-Net must be covered exactly by its power-of-two tiles (tile decode uses shifts, tiles_x/tiles_y
+  // are exact quotients, there are no edge tiles).  A grid like 768 = 3*256 gives 24x24 / 12x12 / 6x6 / 3x3 levels that the
+  // 16x8 boxes do not tile: reject it here instead of rendering garbage (the reference accepts any multiple of 256).
+  for (const auto& L : h->layers) {
+    const Geo g = layer_geo(h, L, B, H, W);
+    const bool pow2 = (g.tw & (g.tw - 1)) == 0 && (g.th & (g.th - 1)) == 0 && (g.nb & (g.nb - 1)) == 0;
+    if (!pow2 || g.tw * g.th * g.nb != kTileM || g.hs % g.th || g.ws % g.tw)
+      return fail(LSPG_EINVAL, "%dx%d is not supported: the %dx%d level does not tile into %dx%d boxes (height and width "
+                  "must be powers of two >= %d)", H, W, g.hs, g.ws, g.tw, g.th, m);
+  }
   return LSPG_OK;
 }
 
@@ -635,7 +644,6 @@ int build_plan(lspg_ctx* h, Plan* P, int B, int H, int W, int mode, void* worksp
   }
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   uint8_t* ws_scratch = ws + align_up(off, 1024);
-  CUDA_TRY(cudaMemset(ws_scratch, 0, kCounterBytes));      // counters return to zero at the end of every layer that uses them
   for (const Layer& L : h->layers) {
     PlanLayer pl;
     ConvParams& p = pl.prm;
@@ -643,9 +651,8 @@ int build_plan(lspg_ctx* h, Plan* P, int B, int H, int W, int mode, void* worksp
     const Geo g = layer_geo(h, L, B, H, W);
     const int Hs = g.hs, Ws = g.ws;
     const int tw = g.tw, th = g.th, nb = g.nb;
-    static const bool no_base_offset = getenv("LSPG_DESC_BASE_OFFSET") == nullptr;
-    // Measured on B200 (gpurun bringup2): the UMMA swizzle phase follows the absolute smem address; setting the
-    // descriptor's base-offset field for a 128-byte-shifted start corrupts the result.  Kept as a debug switch.
+    // Measured on B200 (gpurun bringup2): the UMMA swizzle phase follows the absolute smem address, so a 128-byte-shifted
+    // start needs NO descriptor base offset (setting it corrupts the result).
     pl.patch = g.patch;
     int abox_w = tw, abox_h = th, abox_n = nb;
     if (pl.patch) {
@@ -663,7 +670,7 @@ int build_plan(lspg_ctx* h, Plan* P, int B, int H, int W, int mode, void* worksp
       for (int z = 0; z < L.n_phases; ++z)
         for (int t = 0; t < L.n_taps; ++t)
           p.tap_row[z][t] = static_cast<int16_t>((L.tap_dy[z][t] - p.patch_dy0[z]) * pw + (L.tap_dx[z][t] - p.patch_dx0[z]));
-      p.desc_base_offset = no_base_offset ? 0 : 1;
+      p.desc_base_offset = 0;
       if (pw * ph * 128 > kPatchSlot) return fail(LSPG_EINVAL, "patch %dx%d does not fit its smem slot", pw, ph);
       abox_w = pw; abox_h = ph; abox_n = 1;
     }
@@ -681,20 +688,16 @@ int build_plan(lspg_ctx* h, Plan* P, int B, int H, int W, int mode, void* worksp
     p.n_split = g.n_split; p.split_len = g.split_len;
     p.total_tiles = g.tiles_per_split * g.n_split;
     if (g.pair) {
-      static const bool no_resident = getenv("LSPG_NO_RESIDENT") != nullptr;
       const int n_items = g.k_items * L.n_taps;                           // weight tiles per output tile
       const int stage = (pair_stacked(g.bn, NL) ? 3 : NL) * (g.bn / 2) * 128;
       const int cap = std::min(16, (kSmemBudget - 1024 - 5120 - 2 * NL * kPatchStride) / stage);
-      p.b_resident = (!no_resident && L.n_phases == 1 && g.n_tiles == 1 && n_items <= cap) ? 1 : 0;
+      p.b_resident = (L.n_phases == 1 && g.n_tiles == 1 && n_items <= cap) ? 1 : 0;
     }
-    p.partial = reinterpret_cast<float*>(ws_scratch + kCounterBytes);
-    // Measured on B200: letting the last-arriving CTA sum the partials in-kernel (LSPG_SPLITK_FIXUP=1) is slower than a
-    // separate finisher kernel (B=1: 2.19 vs 1.44 ms per frame) - one CTA's 128 threads reduce a tile far more slowly
-    // than a grid of them - so the two-pass scheme is the default.
-    static const bool two_pass = getenv("LSPG_SPLITK_FIXUP") == nullptr;
-    const bool fix_in_kernel = !two_pass && g.n_split > 1 && static_cast<size_t>(g.tiles_per_split) * sizeof(int) <= kCounterBytes;
-    p.split_counter = fix_in_kernel ? reinterpret_cast<int*>(ws_scratch) : nullptr;
-    pl.split = g.n_split > 1 && !fix_in_kernel;      // two-pass: a finisher kernel follows
+    p.partial = reinterpret_cast<float*>(ws_scratch);
+    // Split-K is two-pass: raw fp32 partials, then splitk_reduce_kernel.  (Measured on B200 in round 1: letting the
+    // last-arriving CTA sum the partials in-kernel was slower - one CTA's epilogue threads reduce a tile far more slowly
+    // than a grid of them - so that variant was removed.)
+    pl.split = g.n_split > 1;
     p.n_taps = L.n_taps; p.n_src = L.n_src;
     p.chunks[0] = L.cin[0] / 64; p.chunks[1] = L.n_src == 2 ? L.cin[1] / 64 : 0;
     p.relu = L.relu; p.has_res = L.res >= 0 ? 1 : 0;
@@ -823,85 +826,106 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
   return launch_pdl_cluster(kernel, grid, block, smem, st, 1, std::forward<Args>(args)...);
 }
 
-template <int BN, int NL, bool TAIL>
-int launch_conv(const ConvParams& p, int grid, cudaStream_t st) {
-  using Cfg = ConvCfg<BN, NL, TAIL>;
-  static bool configured = false;
-  if (!configured) {
-    CUDA_TRY(cudaFuncSetAttribute(conv_umma_kernel<BN, NL, TAIL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  Cfg::kSmemBytes));
-    configured = true;
+// Opt-in to > 48 KB of dynamic shared memory.  The attribute is per (function, device): a process that renders on
+// several GPUs (two modules, or a module moved with .to('cuda:1')) must set it on each of them, so the "done" flag is a
+// bit per device ordinal, not a process-wide bool.
+template <typename K>
+int ensure_smem(K kernel, int bytes, int device, unsigned long long* done_mask) {
+  const unsigned long long bit = 1ull << (device & 63);
+  if (!(*done_mask & bit)) {
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    *done_mask |= bit;
   }
+  return LSPG_OK;
+}
+
+const void* g_last_func = nullptr;     // host stub of the most recent conv launch (identifies graph nodes after capture)
+
+template <int BN, int NL, bool TAIL>
+int launch_conv(const ConvParams& p, int grid, int device, cudaStream_t st) {
+  using Cfg = ConvCfg<BN, NL, TAIL>;
+  static unsigned long long done = 0;
+  int rc = ensure_smem(conv_umma_kernel<BN, NL, TAIL>, Cfg::kSmemBytes, device, &done);
+  if (rc) return rc;
+  g_last_func = reinterpret_cast<const void*>(conv_umma_kernel<BN, NL, TAIL>);
   CUDA_TRY(launch_pdl(conv_umma_kernel<BN, NL, TAIL>, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, st, p));
   return LSPG_OK;
 }
 
-int epi_warps() {     // 4 or 8 epilogue warps for the non-tail patch / pair kernels (A/B switch: LSPG_EPI_WARPS)
-  static const int v = [] { const char* e = getenv("LSPG_EPI_WARPS"); return (e && atoi(e) == 4) ? 4 : 8; }();
-  return v;
-}
-
-template <int BN, int NL, bool TAIL, int CL, int EW>
-int launch_patch(const ConvParams& p, int grid, cudaStream_t st) {
+// Epilogue warps: 4 for the tail (one fp32 / uint8 scatter per pixel), 8 for every other patch / pair kernel.
+template <int BN, int NL, bool TAIL, int CL>
+int launch_patch(const ConvParams& p, int grid, int device, cudaStream_t st) {
   using Cfg = PatchCfg<BN, NL, TAIL>;
-  static bool configured = false;
-  if (!configured) {
-    CUDA_TRY(cudaFuncSetAttribute(conv_patch_kernel<BN, NL, TAIL, CL, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  Cfg::kSmemBytes));
-    configured = true;
-  }
+  constexpr int EW = TAIL ? 4 : 8;
+  static unsigned long long done = 0;
+  int rc = ensure_smem(conv_patch_kernel<BN, NL, TAIL, CL, EW>, Cfg::kSmemBytes, device, &done);
+  if (rc) return rc;
+  g_last_func = reinterpret_cast<const void*>(conv_patch_kernel<BN, NL, TAIL, CL, EW>);
   CUDA_TRY(launch_pdl_cluster(conv_patch_kernel<BN, NL, TAIL, CL, EW>, dim3(grid), dim3(64 + EW * 32), Cfg::kSmemBytes, st, CL, p));
   return LSPG_OK;
 }
 
 template <int BN, int NL, bool TAIL>
-int launch_patch_cl(const ConvParams& p, int grid, int cluster, cudaStream_t st) {
-  if (TAIL || epi_warps() == 4)
-    return cluster == 2 ? launch_patch<BN, NL, TAIL, 2, 4>(p, grid, st) : launch_patch<BN, NL, TAIL, 1, 4>(p, grid, st);
-  return cluster == 2 ? launch_patch<BN, NL, TAIL, 2, (TAIL ? 4 : 8)>(p, grid, st) : launch_patch<BN, NL, TAIL, 1, (TAIL ? 4 : 8)>(p, grid, st);
-}
-
-template <int BN, int NL, int EW, bool STK = false>
-int launch_pair_ew(const ConvParams& p, int grid, cudaStream_t st) {
-  using Cfg = PairCfg<BN, NL, STK>;
-  static bool configured = false;
-  if (!configured) {
-    CUDA_TRY(cudaFuncSetAttribute(conv_pair_kernel<BN, NL, EW, STK>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    configured = true;
-  }
-  CUDA_TRY(launch_pdl_cluster(conv_pair_kernel<BN, NL, EW, STK>, dim3(grid), dim3(64 + EW * 32), Cfg::kSmemBytes, st, 2, p));
-  return LSPG_OK;
+int launch_patch_cl(const ConvParams& p, int grid, int cluster, int device, cudaStream_t st) {
+  return cluster == 2 ? launch_patch<BN, NL, TAIL, 2>(p, grid, device, st) : launch_patch<BN, NL, TAIL, 1>(p, grid, device, st);
 }
 
 template <int BN, int NL>
-int launch_pair(const ConvParams& p, int grid, cudaStream_t st) {
-  if constexpr (BN == 64 && NL == 2) {
-    if (pair_stacked(BN, NL)) return launch_pair_ew<BN, NL, 8, true>(p, grid, st);
-  }
-  return epi_warps() == 4 ? launch_pair_ew<BN, NL, 4>(p, grid, st) : launch_pair_ew<BN, NL, 8>(p, grid, st);
+int launch_pair(const ConvParams& p, int grid, int device, cudaStream_t st) {
+  constexpr bool STK = (BN == 64 && NL == 2);          // must agree with pair_stacked()
+  using Cfg = PairCfg<BN, NL, STK>;
+  static unsigned long long done = 0;
+  int rc = ensure_smem(conv_pair_kernel<BN, NL, 8, STK>, Cfg::kSmemBytes, device, &done);
+  if (rc) return rc;
+  g_last_func = reinterpret_cast<const void*>(conv_pair_kernel<BN, NL, 8, STK>);
+  CUDA_TRY(launch_pdl_cluster(conv_pair_kernel<BN, NL, 8, STK>, dim3(grid), dim3(64 + 8 * 32), Cfg::kSmemBytes, st, 2, p));
+  return LSPG_OK;
 }
 
-int launch_layer(const PlanLayer& pl, int kind, int NL, cudaStream_t st) {
+int launch_layer(const PlanLayer& pl, int kind, int NL, int device, cudaStream_t st) {
   if (pl.pair) {
-    if (pl.bn == 256) return NL == 1 ? launch_pair<256, 1>(pl.prm, pl.grid, st) : launch_pair<256, 2>(pl.prm, pl.grid, st);
-    if (pl.bn == 64) return NL == 1 ? launch_pair<64, 1>(pl.prm, pl.grid, st) : launch_pair<64, 2>(pl.prm, pl.grid, st);
-    return NL == 1 ? launch_pair<128, 1>(pl.prm, pl.grid, st) : launch_pair<128, 2>(pl.prm, pl.grid, st);
+    if (pl.bn == 256) return NL == 1 ? launch_pair<256, 1>(pl.prm, pl.grid, device, st) : launch_pair<256, 2>(pl.prm, pl.grid, device, st);
+    if (pl.bn == 64) return NL == 1 ? launch_pair<64, 1>(pl.prm, pl.grid, device, st) : launch_pair<64, 2>(pl.prm, pl.grid, device, st);
+    return NL == 1 ? launch_pair<128, 1>(pl.prm, pl.grid, device, st) : launch_pair<128, 2>(pl.prm, pl.grid, device, st);
   }
   if (pl.patch) {
     const int c = pl.cluster;
-    if (kind == K_TAIL) return NL == 1 ? launch_patch_cl<16, 1, true>(pl.prm, pl.grid, c, st) : launch_patch_cl<16, 2, true>(pl.prm, pl.grid, c, st);
-    if (pl.bn == 128) return NL == 1 ? launch_patch_cl<128, 1, false>(pl.prm, pl.grid, c, st) : launch_patch_cl<128, 2, false>(pl.prm, pl.grid, c, st);
-    return NL == 1 ? launch_patch_cl<64, 1, false>(pl.prm, pl.grid, c, st) : launch_patch_cl<64, 2, false>(pl.prm, pl.grid, c, st);
+    if (kind == K_TAIL) return NL == 1 ? launch_patch_cl<16, 1, true>(pl.prm, pl.grid, c, device, st) : launch_patch_cl<16, 2, true>(pl.prm, pl.grid, c, device, st);
+    if (pl.bn == 128) return NL == 1 ? launch_patch_cl<128, 1, false>(pl.prm, pl.grid, c, device, st) : launch_patch_cl<128, 2, false>(pl.prm, pl.grid, c, device, st);
+    return NL == 1 ? launch_patch_cl<64, 1, false>(pl.prm, pl.grid, c, device, st) : launch_patch_cl<64, 2, false>(pl.prm, pl.grid, c, device, st);
   }
-  if (kind == K_TAIL) return NL == 1 ? launch_conv<16, 1, true>(pl.prm, pl.grid, st) : launch_conv<16, 2, true>(pl.prm, pl.grid, st);
-  if (pl.bn == 128) return NL == 1 ? launch_conv<128, 1, false>(pl.prm, pl.grid, st) : launch_conv<128, 2, false>(pl.prm, pl.grid, st);
-  return NL == 1 ? launch_conv<64, 1, false>(pl.prm, pl.grid, st) : launch_conv<64, 2, false>(pl.prm, pl.grid, st);
+  if (kind == K_TAIL) return NL == 1 ? launch_conv<16, 1, true>(pl.prm, pl.grid, device, st) : launch_conv<16, 2, true>(pl.prm, pl.grid, device, st);
+  if (pl.bn == 128) return NL == 1 ? launch_conv<128, 1, false>(pl.prm, pl.grid, device, st) : launch_conv<128, 2, false>(pl.prm, pl.grid, device, st);
+  return NL == 1 ? launch_conv<64, 1, false>(pl.prm, pl.grid, device, st) : launch_conv<64, 2, false>(pl.prm, pl.grid, device, st);
+}
+
+// The caller-dependent arguments of the two I/O nodes of a forward (input packer, tail conv).
+struct PackArgs {
+  const float* fm; long long fs; const float* cand; long long cs; int in_nc;
+  __nv_bfloat16* dst; long long limb_stride; int batch, height, width;
+  int blocks;
+};
+
+PackArgs make_pack_args(const lspg_ctx* h, const Plan* P, const IoKey& io) {
+  PackArgs a;
+  a.fm = io.fm; a.fs = io.fm_bstride; a.cand = io.cand; a.cs = io.cand_bstride; a.in_nc = h->in_nc;
+  a.dst = reinterpret_cast<__nv_bfloat16*>(static_cast<uint8_t*>(P->workspace) + P->tensor_off[0]);
+  a.limb_stride = static_cast<long long>(P->tensor_limb_stride[0] / 2);
+  a.batch = P->batch; a.height = P->height; a.width = P->width;
+  const long long total = static_cast<long long>(P->batch) * (P->height / 2) * (P->width / 2);
+  a.blocks = static_cast<int>((total + 127) / 128);
+  if (a.blocks > h->num_sms * 16) a.blocks = h->num_sms * 16;
+  return a;
+}
+
+void set_tail_io(ConvParams* prm, const IoKey& io) {
+  prm->out_f32 = io.u8 ? nullptr : static_cast<float*>(io.out);
+  prm->out_u8 = io.u8 ? static_cast<uint8_t*>(io.out) : nullptr;
 }
 
 // Enqueue every kernel of one forward on `st` (plain stream launches; also the body of the graph capture).
 int enqueue_forward(lspg_ctx* h, Plan* P, const IoKey& io, cudaStream_t st, bool debug_sync, bool profile) {
   const int NL = nl_of(P->mode);
-  const int batch = P->batch, height = P->height, width = P->width;
   int rc;
   std::vector<cudaEvent_t>* evs = nullptr;
   if (profile && h->prof_used < 256) {
@@ -915,27 +939,20 @@ int enqueue_forward(lspg_ctx* h, Plan* P, const IoKey& io, cudaStream_t st, bool
   }
   // 1. input packer (cat + NCHW->NHWC + bf16 + space-to-depth)
   {
-    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(static_cast<uint8_t*>(P->workspace) + P->tensor_off[0]);
-    const long long limb_stride = static_cast<long long>(P->tensor_limb_stride[0] / 2);
-    const long long total = static_cast<long long>(batch) * (height / 2) * (width / 2);
-    int blocks = static_cast<int>((total + 127) / 128);
-    if (blocks > h->num_sms * 16) blocks = h->num_sms * 16;
-    const long long fs = io.fm_bstride, cs = io.cand_bstride;
+    const PackArgs a = make_pack_args(h, P, io);
     if (NL == 1)
-      CUDA_TRY(launch_pdl(pack_input_s2d_kernel<1>, dim3(blocks), dim3(128), 0, st, io.fm, fs, io.cand, cs, h->in_nc, dst, limb_stride, batch, height, width));
+      CUDA_TRY(launch_pdl(pack_input_s2d_kernel<1>, dim3(a.blocks), dim3(128), 0, st, a.fm, a.fs, a.cand, a.cs, a.in_nc, a.dst, a.limb_stride, a.batch, a.height, a.width));
     else
-      CUDA_TRY(launch_pdl(pack_input_s2d_kernel<2>, dim3(blocks), dim3(128), 0, st, io.fm, fs, io.cand, cs, h->in_nc, dst, limb_stride, batch, height, width));
+      CUDA_TRY(launch_pdl(pack_input_s2d_kernel<2>, dim3(a.blocks), dim3(128), 0, st, a.fm, a.fs, a.cand, a.cs, a.in_nc, a.dst, a.limb_stride, a.batch, a.height, a.width));
     if (debug_sync) CUDA_TRY(cudaStreamSynchronize(st));
     if (evs) CUDA_TRY(cudaEventRecord((*evs)[1], st));
   }
   // 2. conv stack
   for (size_t i = 0; i < h->layers.size(); ++i) {
     PlanLayer& pl = P->layers[i];
-    if (h->layers[i].kind == K_TAIL) {
-      pl.prm.out_f32 = io.u8 ? nullptr : static_cast<float*>(io.out);
-      pl.prm.out_u8 = io.u8 ? static_cast<uint8_t*>(io.out) : nullptr;
-    }
-    if ((rc = launch_layer(pl, h->layers[i].kind, NL, st))) return rc;
+    if (h->layers[i].kind == K_TAIL) set_tail_io(&pl.prm, io);
+    if ((rc = launch_layer(pl, h->layers[i].kind, NL, h->device, st))) return rc;
+    if (h->layers[i].kind == K_TAIL) h->tail_func = g_last_func;
     if (pl.split) {
       CUDA_TRY(launch_pdl(splitk_reduce_kernel, dim3(pl.red_blocks), dim3(128), 0, st, pl.red));
     }
@@ -947,6 +964,69 @@ int enqueue_forward(lspg_ctx* h, Plan* P, const IoKey& io, cudaStream_t st, bool
                     h->layers[i].conv_key.c_str(), pl.bn, pl.grid, pl.prm.total_tiles, cudaGetErrorString(e));
     }
   }
+  return LSPG_OK;
+}
+
+void free_plan_graph(Plan* P) {
+  if (P->exec) cudaGraphExecDestroy(P->exec);
+  if (P->graph) cudaGraphDestroy(P->graph);
+  P->exec = nullptr; P->graph = nullptr; P->pack_node = P->tail_node = nullptr;
+}
+
+// Capture one forward with `io` baked in, instantiate it, and find the two nodes that carry the caller's pointers.
+int capture_plan_graph(lspg_ctx* h, Plan* P, const IoKey& io) {
+  const int NL = nl_of(P->mode);
+  if (!h->capture_stream) CUDA_TRY(cudaStreamCreateWithFlags(&h->capture_stream, cudaStreamNonBlocking));
+  cudaGraph_t graph = nullptr;
+  CUDA_TRY(cudaStreamBeginCapture(h->capture_stream, cudaStreamCaptureModeThreadLocal));
+  int rc = enqueue_forward(h, P, io, h->capture_stream, false, false);
+  cudaError_t ce = cudaStreamEndCapture(h->capture_stream, &graph);
+  if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+  if (ce != cudaSuccess) return fail(LSPG_ECUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(ce));
+  cudaGraphExec_t exec = nullptr;
+  ce = cudaGraphInstantiate(&exec, graph, 0);
+  if (ce != cudaSuccess) { cudaGraphDestroy(graph); return fail(LSPG_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce)); }
+  P->graph = graph; P->exec = exec; P->io = io;
+  P->pack_node = P->tail_node = nullptr;
+  // identify the packer and tail nodes by their kernel function (each occurs exactly once per forward)
+  const void* pack_func = NL == 1 ? reinterpret_cast<const void*>(pack_input_s2d_kernel<1>)
+                                  : reinterpret_cast<const void*>(pack_input_s2d_kernel<2>);
+  size_t n = 0;
+  if (cudaGraphGetNodes(graph, nullptr, &n) == cudaSuccess && n > 0) {
+    std::vector<cudaGraphNode_t> nodes(n);
+    if (cudaGraphGetNodes(graph, nodes.data(), &n) == cudaSuccess) {
+      for (size_t i = 0; i < n; ++i) {
+        cudaGraphNodeType ty;
+        if (cudaGraphNodeGetType(nodes[i], &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) continue;
+        cudaKernelNodeParams np{};
+        if (cudaGraphKernelNodeGetParams(nodes[i], &np) != cudaSuccess) continue;
+        if (np.func == pack_func) { P->pack_node = nodes[i]; P->pack_np = np; }
+        else if (np.func == h->tail_func) { P->tail_node = nodes[i]; P->tail_np = np; }
+      }
+    }
+  }
+  cudaGetLastError();      // a failed query above only disables in-place updates (the next pointer change re-captures)
+  ++h->n_captures;
+  return LSPG_OK;
+}
+
+// Patch the caller's pointers into the instantiated graph (input packer arguments, tail ConvParams).
+int update_graph_io(lspg_ctx* h, Plan* P, const IoKey& io) {
+  if (!P->pack_node || !P->tail_node) return fail(LSPG_ECUDA, "graph nodes of the packer / tail conv were not identified");
+  PackArgs a = make_pack_args(h, P, io);
+  void* pargs[10] = {&a.fm, &a.fs, &a.cand, &a.cs, &a.in_nc, &a.dst, &a.limb_stride, &a.batch, &a.height, &a.width};
+  cudaKernelNodeParams np = P->pack_np;
+  np.kernelParams = pargs; np.extra = nullptr;
+  CUDA_TRY(cudaGraphExecKernelNodeSetParams(P->exec, P->pack_node, &np));
+  ConvParams prm = P->layers.back().prm;
+  set_tail_io(&prm, io);
+  void* targs[1] = {&prm};
+  np = P->tail_np;
+  np.kernelParams = targs; np.extra = nullptr;
+  CUDA_TRY(cudaGraphExecKernelNodeSetParams(P->exec, P->tail_node, &np));
+  P->layers.back().prm = prm;
+  P->io = io;
+  ++h->n_io_updates;
   return LSPG_OK;
 }
 
@@ -1005,8 +1085,7 @@ int lspg_destroy(lspg_handle h) {
     }
     for (auto& set : h->prof_events)
       for (auto& e : set) cudaEventDestroy(e);
-    for (auto& kv : h->plans)
-      for (auto& ge : kv.second->graphs) cudaGraphExecDestroy(ge.exec);
+    for (auto& kv : h->plans) free_plan_graph(kv.second.get());
     if (h->capture_stream) cudaStreamDestroy(h->capture_stream);
     if (h->trace_buf) cudaFree(h->trace_buf);
   }
@@ -1041,6 +1120,7 @@ int lspg_load_weights(lspg_handle h, const lspg_tensor* tensors, int n) {
     bool changed = false;
     int rc;
     if (L.w.empty()) { L.w.assign(wn, 0.0f); changed = true; }
+    if (by_name.count(L.conv_key + ".weight")) L.has_w = true;
     if ((rc = take(L.conv_key + ".weight", L.w, wn, &changed))) return rc;
     if (L.has_bn) {
       if (L.bn_w.empty()) { L.bn_w.assign(L.cout, 1.f); L.bn_b.assign(L.cout, 0.f); L.bn_m.assign(L.cout, 0.f); L.bn_v.assign(L.cout, 1.f); }
@@ -1076,6 +1156,10 @@ static int forward_impl(lspg_handle h, const float* feature_map, int64_t fm_bstr
   if (!h) return fail(LSPG_EINVAL, "null handle");
   if (h->device < 0) return fail(LSPG_ENODEV, "host-only handle: lspg_forward needs an sm_100 device (no CPU path exists)");
   if (!h->weights_loaded) return fail(LSPG_ESTATE, "lspg_load_weights has not been called");
+  for (const auto& L : h->layers)
+    if (!L.has_w)
+      return fail(LSPG_ESTATE, "weights incomplete: %s.weight was never loaded (a forward with zero-filled convs would render "
+                  "black frames; nn.DataParallel replicas do not carry parameters - use parallel.ShardedRenderer)", L.conv_key.c_str());
   if (!feature_map || !out || !workspace || (h->in_nc > 1 && !cand)) return fail(LSPG_EINVAL, "null buffer");
   int rc = check_shape(h, batch, height, width, mode);
   if (rc) return rc;
@@ -1088,47 +1172,38 @@ static int forward_impl(lspg_handle h, const float* feature_map, int64_t fm_bstr
   if (it == h->plans.end()) {
     std::unique_ptr<Plan> P(new Plan);
     if ((rc = build_plan(h, P.get(), batch, height, width, mode, workspace))) return rc;
-    if (h->plans.size() > 16) {
-      for (auto& kv : h->plans)
-        for (auto& ge : kv.second->graphs) cudaGraphExecDestroy(ge.exec);
-      h->plans.clear();
-      h->last_plan = nullptr;
+    if (h->plans.size() >= 16) {           // bounded: drop the least recently used plan (and its graph)
+      auto victim = h->plans.begin();
+      for (auto jt = h->plans.begin(); jt != h->plans.end(); ++jt)
+        if (jt->second->last_use < victim->second->last_use) victim = jt;
+      if (h->last_plan == victim->second.get()) h->last_plan = nullptr;
+      free_plan_graph(victim->second.get());
+      h->plans.erase(victim);
     }
     it = h->plans.emplace(key, std::move(P)).first;
   }
   Plan* P = it->second.get();
+  P->last_use = ++h->use_clock;
   h->last_plan = P;
   IoKey io{feature_map, fm_bstride, cand, cand_bstride, out, out_is_u8};
   static const bool no_graph = getenv("LSPG_NO_GRAPH") != nullptr;
   static const bool debug_sync = getenv("LSPG_DEBUG_SYNC") != nullptr;   // per-layer sync + error attribution (bring-up)
   if (no_graph || debug_sync || h->profiling) return enqueue_forward(h, P, io, st, debug_sync, h->profiling);
 
-  // CUDA-graph replay: the ~80-120 launches of one forward are captured once per (plan, I/O pointers) on a private
-  // stream (the caller's stream may be the legacy default stream, which cannot be captured) and replayed with a
-  // single cudaGraphLaunch on the caller's stream.
-  for (auto& ge : P->graphs)
-    if (ge.io == io) {
-      CUDA_TRY(cudaGraphLaunch(ge.exec, st));
-      return LSPG_OK;
+  // CUDA-graph replay: the ~80-120 launches of one forward are captured ONCE per plan on a private stream (the caller's
+  // stream may be the legacy default stream, which cannot be captured) and replayed with a single cudaGraphLaunch on the
+  // caller's stream.  When a call brings other I/O pointers than the ones baked into the instantiated graph, only the
+  // two nodes that hold them (input packer, tail conv) are patched - no re-capture, no re-instantiation.
+  if (P->exec && !(P->io == io)) {
+    if (update_graph_io(h, P, io) != LSPG_OK) {       // should not happen; keep the call correct by re-capturing
+      ++h->n_recaptures;
+      free_plan_graph(P);
     }
-  if (!h->capture_stream) CUDA_TRY(cudaStreamCreateWithFlags(&h->capture_stream, cudaStreamNonBlocking));
-  cudaGraph_t graph = nullptr;
-  CUDA_TRY(cudaStreamBeginCapture(h->capture_stream, cudaStreamCaptureModeThreadLocal));
-  rc = enqueue_forward(h, P, io, h->capture_stream, false, false);
-  cudaError_t ce = cudaStreamEndCapture(h->capture_stream, &graph);
-  if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
-  if (ce != cudaSuccess) return fail(LSPG_ECUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(ce));
-  GraphEntry ge;
-  ge.io = io;
-  ce = cudaGraphInstantiate(&ge.exec, graph, 0);
-  cudaGraphDestroy(graph);
-  if (ce != cudaSuccess) return fail(LSPG_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
-  if (P->graphs.size() >= 16) {                      // bounded cache: drop the oldest instantiation
-    cudaGraphExecDestroy(P->graphs.front().exec);
-    P->graphs.erase(P->graphs.begin());
   }
-  P->graphs.push_back(ge);
-  CUDA_TRY(cudaGraphLaunch(ge.exec, st));
+  if (!P->exec) {
+    if ((rc = capture_plan_graph(h, P, io))) return rc;
+  }
+  CUDA_TRY(cudaGraphLaunch(P->exec, st));
   return LSPG_OK;
 }
 
@@ -1274,6 +1349,30 @@ int lspg_debug_read_trace(lspg_handle h, uint64_t* dst, int64_t count) {
   CUDA_TRY(cudaSetDevice(h->device));
   CUDA_TRY(cudaDeviceSynchronize());
   CUDA_TRY(cudaMemcpy(dst, h->trace_buf, sizeof(uint64_t) * count, cudaMemcpyDeviceToHost));
+  return LSPG_OK;
+}
+
+int lspg_graph_stats(lspg_handle h, int64_t* captures, int64_t* io_updates, int64_t* recaptures) {
+  if (!h || !captures || !io_updates || !recaptures) return fail(LSPG_EINVAL, "null argument");
+  *captures = h->n_captures; *io_updates = h->n_io_updates; *recaptures = h->n_recaptures;
+  return LSPG_OK;
+}
+
+int lspg_release_workspace(lspg_handle h, void* workspace) {
+  if (!h) return fail(LSPG_EINVAL, "null handle");
+  if (h->device >= 0) {
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaDeviceSynchronize());            // forwards that still use the workspace finish before their plan goes
+  }
+  for (auto it = h->plans.begin(); it != h->plans.end();) {
+    if (workspace == nullptr || std::get<4>(it->first) == workspace) {
+      if (h->last_plan == it->second.get()) h->last_plan = nullptr;
+      free_plan_graph(it->second.get());
+      it = h->plans.erase(it);
+    } else {
+      ++it;
+    }
+  }
   return LSPG_OK;
 }
 

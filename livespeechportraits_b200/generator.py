@@ -62,6 +62,7 @@ class Feature2Face_G(nn.Module):
         self._device_index: Optional[int] = None
         self._weights_dirty = True
         self._workspaces: Dict[Tuple[int, int, int, int, int], torch.Tensor] = {}
+        self._host_handle = None
         # host-only handle: gives the layer list (keys, shapes) without needing a GPU
         plan = C.c_void_p()
         _lib.check(self._lib.lspg_create(C.byref(plan), _lib.LSPG_VARIANT[size], self.ngf, self.num_downs, self.in_nc,
@@ -118,6 +119,43 @@ class Feature2Face_G(nn.Module):
         self._weights_dirty = True
         return super().train(mode)
 
+    # ------------------------------------------------------------------ copies, replicas, pickling
+    # The native handle (packed weights, plans, CUDA graphs) and the workspaces belong to ONE module object.  A shallow
+    # copy that shared them would double-free the handle; so every way of copying the module resets the native state and
+    # the copy re-creates its own handle on first use.
+    _NATIVE_STATE = ("_lib", "_handle", "_host_handle", "_workspaces", "_device_index", "_weights_dirty")
+
+    def __getstate__(self):
+        d = self.__dict__.copy()
+        for k in self._NATIVE_STATE:
+            d.pop(k, None)
+        return d
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._lib = _lib.load()
+        self._handle = C.c_void_p()
+        self._host_handle = None
+        self._device_index = None
+        self._weights_dirty = True
+        self._workspaces = {}
+
+    def __deepcopy__(self, memo):
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        new.__setstate__(copy.deepcopy(self.__getstate__(), memo))
+        return new
+
+    def _replicate_for_data_parallel(self):
+        # nn.DataParallel with more than one device id shallow-copies __dict__ (shared native handle) and strips the
+        # parameters from the replicas (they would upload empty weights).  The reference's multi-GPU hook
+        # (models/networks.py:392-401) is replaced by one process per GPU: parallel.ShardedRenderer.
+        raise NotImplementedError(
+            "Feature2Face_G (B200) cannot be replicated by nn.DataParallel over several devices: the module owns a native "
+            "handle per device.  Wrap it with device_ids=[one id] (what demo.py does) or shard frames over processes with "
+            "livespeechportraits_b200.parallel.ShardedRenderer")
+
     def _ensure_handle(self, device: torch.device) -> None:
         if device.type != "cuda":
             raise RuntimeError("livespeechportraits_b200 has no CPU path: inputs must live on a B200 (sm_100) device")
@@ -125,6 +163,7 @@ class Feature2Face_G(nn.Module):
         if self._handle and self._device_index == idx:
             return
         if self._handle:
+            self._drop_workspaces()
             self._lib.lspg_destroy(self._handle)
             self._handle = C.c_void_p()
         h = C.c_void_p()
@@ -152,16 +191,29 @@ class Feature2Face_G(nn.Module):
         self._weights_dirty = False
 
     # ------------------------------------------------------------------ forward
+    MAX_WORKSPACES = 4
+
+    def _drop_workspaces(self) -> None:
+        if self._handle and self._workspaces:
+            _lib.check(self._lib.lspg_release_workspace(self._handle, None))     # waits for the device, drops every plan
+        self._workspaces.clear()
+
     def _workspace(self, batch: int, height: int, width: int, mode: int) -> torch.Tensor:
+        """Caller-owned scratch of one problem size, LRU-cached.  Before a workspace is released the library is told
+        (lspg_release_workspace: device sync + the plans / graphs that point into it are dropped), so no kernel that is
+        still in flight on another stream can see its memory reused."""
         key = (batch, height, width, mode, self._device_index)
-        ws = self._workspaces.get(key)
+        ws = self._workspaces.pop(key, None)
         if ws is None:
             need = C.c_size_t()
             _lib.check(self._lib.lspg_workspace_bytes(self._handle, batch, height, width, mode, C.byref(need)))
+            while len(self._workspaces) >= self.MAX_WORKSPACES:
+                old_key = next(iter(self._workspaces))               # least recently used (dict keeps insertion order)
+                old = self._workspaces.pop(old_key)
+                _lib.check(self._lib.lspg_release_workspace(self._handle, old.data_ptr()))
+                del old
             ws = torch.empty(need.value, dtype=torch.uint8, device=torch.device("cuda", self._device_index))
-            if len(self._workspaces) >= 4:
-                self._workspaces.clear()
-            self._workspaces[key] = ws
+        self._workspaces[key] = ws                                   # (re)insert as most recently used
         return ws
 
     def render_image(self, feature_map: torch.Tensor, cand_image: Optional[torch.Tensor], out: Optional[torch.Tensor] = None,
@@ -186,14 +238,14 @@ class Feature2Face_G(nn.Module):
         if cand_image is None:
             if feature_map.dim() != 4 or feature_map.shape[1] != self.in_nc:
                 raise ValueError(f"expected [B,{self.in_nc},H,W] input, got {tuple(feature_map.shape)}")
-            x = feature_map.contiguous()
+            x = self._aligned(feature_map.contiguous())
             b, _, h, w = x.shape
             fm_ptr, fm_stride = x.data_ptr(), self.in_nc * h * w
             cand_ptr, cand_stride = x.data_ptr() + 4 * h * w, self.in_nc * h * w
             hold = (x,)
         else:
-            fm = feature_map.contiguous()
-            cd = cand_image.contiguous()
+            fm = self._aligned(feature_map.contiguous())
+            cd = self._aligned(cand_image.contiguous())
             b, c1, h, w = fm.shape
             if c1 != 1 or cd.shape[1] != self.in_nc - 1 or cd.shape[2:] != fm.shape[2:] or cd.shape[0] not in (1, b):
                 raise ValueError(f"expected [B,1,H,W] + [B|1,{self.in_nc - 1},H,W], got {tuple(fm.shape)} + {tuple(cd.shape)}")
@@ -205,16 +257,36 @@ class Feature2Face_G(nn.Module):
         mode = _lib.LSPG_MODE[precision or self.precision]
         ws = self._workspace(b, h, w, mode)
         oshape, odtype = ((b, h, w, self.out_nc), torch.uint8) if _uint8 else ((b, self.out_nc, h, w), torch.float32)
+        user_out = None
         if out is None:
             out = torch.empty(oshape, dtype=odtype, device=feature_map.device)
         elif tuple(out.shape) != oshape or out.dtype != odtype or not out.is_contiguous():
             raise ValueError(f"out must be a contiguous {odtype} tensor of shape {oshape}")
+        elif out.device != feature_map.device:
+            raise ValueError(f"out is on {out.device}, the inputs are on {feature_map.device}: the kernels write `out` through a raw pointer")
+        elif out.data_ptr() % 8:
+            # the tail kernel stores float2 / 2-byte pairs: a view at an odd storage offset goes through a temporary
+            user_out, out = out, torch.empty(oshape, dtype=odtype, device=feature_map.device)
         stream = torch.cuda.current_stream(feature_map.device).cuda_stream
         fn = self._lib.lspg_forward_image if _uint8 else self._lib.lspg_forward
         _lib.check(fn(self._handle, fm_ptr, fm_stride, cand_ptr, cand_stride, out.data_ptr(), b, h, w,
                       ws.data_ptr(), ws.numel(), mode, stream))
         del hold
+        if user_out is not None:
+            user_out.copy_(out)
+            return user_out
         return out
+
+    @staticmethod
+    def _aligned(t: torch.Tensor) -> torch.Tensor:
+        """The input packer reads float2: a contiguous view that starts at an odd element of its storage is copied."""
+        return t if t.data_ptr() % 8 == 0 else t.clone()
+
+    def graph_stats(self) -> dict:
+        """CUDA-graph bookkeeping of the native handle: captures, in-place I/O pointer updates, forced re-captures."""
+        a, b_, c = C.c_int64(), C.c_int64(), C.c_int64()
+        _lib.check(self._lib.lspg_graph_stats(self._handle, C.byref(a), C.byref(b_), C.byref(c)))
+        return {"captures": a.value, "io_updates": b_.value, "recaptures": c.value}
 
     def draw_feature_maps(self, landmarks: torch.Tensor, shoulders: Optional[torch.Tensor] = None,
                           size: tuple = (512, 512), out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -238,8 +310,9 @@ class Feature2Face_G(nn.Module):
             sh, n_sh = shoulders.contiguous(), shoulders.shape[1]
         if out is None:
             out = torch.empty((b, 1, h, w), dtype=torch.float32, device=landmarks.device)
-        elif tuple(out.shape) != (b, 1, h, w) or out.dtype != torch.float32 or not out.is_contiguous():
-            raise ValueError(f"out must be a contiguous fp32 tensor of shape {(b, 1, h, w)}")
+        elif tuple(out.shape) != (b, 1, h, w) or out.dtype != torch.float32 or not out.is_contiguous() \
+                or out.device != landmarks.device:
+            raise ValueError(f"out must be a contiguous fp32 tensor of shape {(b, 1, h, w)} on {landmarks.device}")
         stream = torch.cuda.current_stream(landmarks.device).cuda_stream
         _lib.check(self._lib.lspg_draw_feature_maps(self._handle, lm.data_ptr(), sh.data_ptr() if sh is not None else None, n_sh,
                                                     out.data_ptr(), b, h, w, stream))
@@ -317,6 +390,7 @@ class Feature2Face_G(nn.Module):
         try:
             if getattr(self, "_handle", None):
                 self._lib.lspg_destroy(self._handle)
+                self._handle = C.c_void_p()
             if getattr(self, "_host_handle", None):
                 self._lib.lspg_destroy(self._host_handle)
         except Exception:

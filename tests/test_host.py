@@ -254,3 +254,67 @@ def test_planner_picks_the_n_tile_with_fewer_waves():
     assert bn_of(32, 512, 32) == {128}        # 4 vs 7 half-size
     # the 64-channel layers always take the resident-weights N=64 pair kernel
     assert bn_of(16, 64, 256) == {64}
+
+
+@pytest.mark.parametrize("variant", ["normal", "large"])
+def test_accepted_shapes_tile_every_level_and_768_is_rejected(variant):
+    """check_shape (csrc/lspg.cu): a shape is accepted only if the tiles of every layer cover its grid exactly.  768x768 is a
+    multiple of 256 (the reference renders it) but its 24/12/6/3-pixel levels do not tile into the power-of-two boxes: it must
+    be refused with LSPG_EINVAL, not rendered wrong."""
+    lib = _lib.load()
+    h = C.c_void_p()
+    assert lib.lspg_create(C.byref(h), _lib.LSPG_VARIANT[variant], 64, 8, 13, 3, -1) == 0
+    need = C.c_size_t()
+    for (hh, ww) in [(768, 768), (512, 768), (768, 256), (1280, 1024)]:
+        assert lib.lspg_workspace_bytes(h, 1, hh, ww, 1, C.byref(need)) == -1, (hh, ww)
+        assert b"not supported" in lib.lspg_last_error()
+        g = _lib.LspgLayerGeo()
+        assert lib.lspg_debug_layer_geo(h, 0, 1, hh, ww, C.byref(g)) == -1
+    n = C.c_int()
+    lib.lspg_num_layers(h, C.byref(n))
+    for (hh, ww) in [(256, 256), (512, 512), (512, 256), (256, 1024), (1024, 1024), (2048, 512)]:
+        for batch in (1, 3, 32):
+            assert lib.lspg_workspace_bytes(h, batch, hh, ww, 1, C.byref(need)) == 0, (hh, ww, lib.lspg_last_error())
+            for i in range(n.value):
+                g = _lib.LspgLayerGeo()
+                info = _lib.LspgLayerInfo()
+                assert lib.lspg_debug_layer_geo(h, i, batch, hh, ww, C.byref(g)) == 0
+                assert lib.lspg_layer_info_get(h, i, C.byref(info)) == 0
+                c, th, tw = C.c_int(), C.c_int(), C.c_int()
+                # sampling grid of the layer = its first source for upsample/tail convs, its output otherwise
+                tid = info.src[0] if info.kind in (3, 4) else info.out
+                assert lib.lspg_tensor_shape(h, tid, hh, ww, C.byref(c), C.byref(th), C.byref(tw)) == 0
+                grid = th.value * tw.value * batch
+                assert th.value % g.tile_h == 0 and tw.value % g.tile_w == 0
+                assert g.m_tiles * 128 >= grid                                 # tiles cover the grid (image padding only)
+                assert g.m_tiles == (tw.value // g.tile_w) * (th.value // g.tile_h) * -(-batch // g.tile_n)
+    lib.lspg_destroy(h)
+
+
+def test_module_copies_do_not_share_the_native_handle():
+    """copy.deepcopy / pickling reset the native state (a shared handle would be destroyed twice); DataParallel replication
+    over several devices is refused with a pointer to the process-per-GPU path."""
+    import copy
+    import pickle
+    net = Feature2Face_G(opt("normal")).eval()
+    net.load_state_dict(O.make_state_dict("normal", "B"))
+    net._info_handle()                                   # creates a host-only native handle
+    assert net._host_handle
+    for clone in (copy.deepcopy(net), pickle.loads(pickle.dumps(net))):
+        assert not clone._handle and not clone._host_handle and clone._workspaces == {} and clone._weights_dirty
+        assert not clone.training
+        a, b = net.state_dict(), clone.state_dict()
+        assert list(a) == list(b) and all(torch.equal(a[k], b[k]) for k in a)
+        assert all(p is not q for p, q in zip(net.parameters(), clone.parameters()))
+        assert clone.launches_per_forward() == net.launches_per_forward()       # the copy builds its own handle on demand
+        assert clone._host_handle and clone._host_handle.value != net._host_handle.value
+    with pytest.raises(NotImplementedError, match="ShardedRenderer"):
+        net._replicate_for_data_parallel()
+    with pytest.raises(NotImplementedError, match="ShardedRenderer"):
+        torch.nn.parallel.replicate(net, [0, 1]) if torch.cuda.device_count() > 1 else net._replicate_for_data_parallel()
+
+
+def test_package_exports_public_names():
+    import livespeechportraits_b200 as pkg
+    for name in ("Feature2Face_G", "install", "ClipRenderer", "ShardedRenderer", "partition"):
+        assert hasattr(pkg, name)

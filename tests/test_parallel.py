@@ -34,7 +34,13 @@ def _fake_render(fm, out):
     out.copy_(m * torch.tensor([1.0, 2.0, 3.0]).view(1, 3, 1, 1) + fm)
 
 
-def _worker(rank, world, port, n_total, chunk, gather, q):
+def _fake_render_u8(fm, out):
+    # uint8 HWC stand-in for Feature2Face_G.render_image
+    m = (fm.mean(dim=(1, 2, 3)) * 200).to(torch.uint8).view(-1, 1, 1, 1)
+    out.copy_(m + (fm[:, 0, :, :, None] * 50).to(torch.uint8) + torch.tensor([0, 1, 2], dtype=torch.uint8).view(1, 1, 1, 3))
+
+
+def _worker(rank, world, port, n_total, chunk, gather, uint8, to_host, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -42,14 +48,20 @@ def _worker(rank, world, port, n_total, chunk, gather, q):
         g = torch.Generator().manual_seed(7)
         clip = torch.rand(n_total, 1, 8, 8, generator=g)
         s, e = partition(n_total, world, rank)
-        r = ShardedRenderer(_fake_render, chunk=chunk)
-        out = r.render(n_total, clip[s:e].clone(), gather=gather)
-        exp = torch.empty(n_total, 3, 8, 8)
-        _fake_render(clip, exp)
+        fn = _fake_render_u8 if uint8 else _fake_render
+        r = ShardedRenderer(fn, chunk=chunk, uint8=uint8)
+        exp = torch.empty((n_total, 8, 8, 3), dtype=torch.uint8) if uint8 else torch.empty(n_total, 3, 8, 8)
+        fn(clip, exp)
+        host = torch.zeros_like(exp) if to_host else None
+        out = r.render(n_total, clip[s:e].clone(), gather=gather, host_out=host)
         if gather:
-            ok = torch.equal(out, exp)
+            ok = torch.equal(out, exp) and r.gather_mode == "nccl"       # CPU tensors: the collective path (gloo here)
+            if to_host and rank == 0:
+                ok = ok and torch.equal(host, exp)                       # frames delivered to the host in clip order
         else:
             ok = torch.equal(out, exp[s:e])
+        again = r.render(n_total, clip[s:e].clone(), gather=gather)      # the renderer is reusable
+        ok = ok and torch.equal(again, exp if gather else exp[s:e])
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
@@ -61,12 +73,15 @@ def _free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("world,n_total,chunk,gather", [(2, 11, 3, True), (3, 10, 4, True), (2, 5, 8, True), (2, 6, 2, False)])
-def test_sharded_render_gloo(world, n_total, chunk, gather):
+@pytest.mark.parametrize("world,n_total,chunk,gather,uint8,to_host", [
+    (2, 11, 3, True, False, False), (3, 10, 4, True, False, True), (2, 5, 8, True, True, True), (2, 6, 2, False, False, False),
+    (2, 1, 4, True, True, False),       # fewer frames than ranks: rank 1 renders nothing but still takes part in the gather
+])
+def test_sharded_render_gloo(world, n_total, chunk, gather, uint8, to_host):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n_total, chunk, gather, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_total, chunk, gather, uint8, to_host, q)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
@@ -74,3 +89,11 @@ def test_sharded_render_gloo(world, n_total, chunk, gather):
         assert p.exitcode == 0
     results = sorted(q.get(timeout=5) for _ in range(world))
     assert results == [(r, True) for r in range(world)]
+
+
+def test_gather_mode_argument_is_validated():
+    with pytest.raises(ValueError):
+        ShardedRenderer(_fake_render, gather="smoke-signals")
+    r = ShardedRenderer(_fake_render, gather="ce")          # single process: world 1, nothing to gather
+    out = r.render(3, torch.rand(3, 1, 8, 8))
+    assert out.shape == (3, 3, 8, 8) and r.gather_mode is None
