@@ -36,11 +36,14 @@ class ClipRenderer:
         return self._fm, self._out
 
     def render_clip_from_landmarks(self, landmarks_host: torch.Tensor, shoulders_host: Optional[torch.Tensor],
-                                   cand_device: torch.Tensor, out_host: torch.Tensor, size: tuple = (512, 512)) -> torch.Tensor:
+                                   cand_device: torch.Tensor, out_host: torch.Tensor, size: tuple = (512, 512),
+                                   on_batch=None) -> torch.Tensor:
         """Same loop with the feature maps drawn on the GPU (``Feature2Face_G.draw_feature_maps``, the batched replacement of
         datasets/face_dataset.py:276-323): per frame 728 bytes of landmark / shoulder tracks cross PCIe instead of a 1 MB map.
         ``landmarks_host`` [N,73,2] and ``shoulders_host`` [N,2k,2] (or None) are fp32; the whole clip's tracks (a few hundred
-        KB) are uploaded once, batches are rasterised on the compute stream right before their generator pass."""
+        KB) are uploaded once, batches are rasterised on the compute stream right before their generator pass.
+        ``on_batch(offset, length)`` (optional) is called on the host as soon as the frames ``out_host[offset:offset+length]``
+        have landed, in clip order, while later batches are still rendering (the video writer of video.py hangs here)."""
         n = landmarks_host.shape[0]
         w, h = int(size[0]), int(size[1])
         if tuple(out_host.shape) != ((n, h, w, 3) if self.uint8 else (n, 3, h, w)) or not out_host.is_pinned():
@@ -51,6 +54,7 @@ class ClipRenderer:
             s.wait_stream(caller)
         per_frame_cand = cand_device.shape[0] == n and n > 1
         d2h_done = [None, None]
+        landed = []
         with torch.cuda.stream(self._compute):
             lm_dev = landmarks_host.to(self.device, non_blocking=True)
             sh_dev = shoulders_host.to(self.device, non_blocking=True) if shoulders_host is not None else None
@@ -72,6 +76,11 @@ class ClipRenderer:
                 dn = torch.cuda.Event()
                 dn.record(self._d2h)
                 d2h_done[j] = dn
+                landed.append((off, ln, dn))
+        if on_batch is not None:
+            for off, ln, dn in landed:
+                dn.synchronize()
+                on_batch(off, ln)
         self._d2h.synchronize()
         caller.wait_stream(self._compute)
         return out_host
