@@ -19,6 +19,15 @@ SYMBOLS = [
     "lspg_graph_stats", "lspg_release_workspace",
 ]
 
+# include/lsph.h (Audio2Headpose generation loop)
+SYMBOLS_H = ["lsph_create", "lsph_load_weights", "lsph_generate", "lsph_receptive_field", "lsph_debug_packed", "lsph_destroy",
+             "lsph_last_error"]
+
+
+class LsphConfig(C.Structure):
+    _fields_ = [(k, C.c_int) for k in ("apc_hidden", "frame_future", "layers", "blocks", "residual_ch", "dilation_ch", "skip_ch",
+                                       "kernel_size", "use_bias", "cond_ch", "input_ch", "ncenter", "ndim", "loss_gmm")]
+
 
 class LspgTensor(C.Structure):
     _fields_ = [("name", C.c_char_p), ("data", C.POINTER(C.c_float)), ("numel", C.c_int64)]
@@ -104,6 +113,17 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     for name in SYMBOLS:
         if name != "lspg_last_error":
             getattr(lib, name).restype = C.c_int
+    lib.lsph_last_error.restype = C.c_char_p
+    lib.lsph_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(LsphConfig), C.c_int]
+    lib.lsph_load_weights.argtypes = [C.c_void_p, C.POINTER(LspgTensor), C.c_int]
+    lib.lsph_generate.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p,
+                                  C.c_void_p, C.c_int, C.c_void_p]
+    lib.lsph_receptive_field.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+    lib.lsph_destroy.argtypes = [C.c_void_p]
+    lib.lsph_debug_packed.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]
+    for name in SYMBOLS_H:
+        if name != "lsph_last_error":
+            getattr(lib, name).restype = C.c_int
     _LIB = lib
     return lib
 
@@ -111,3 +131,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
 def check(code: int) -> None:
     if code != 0:
         raise LspgError(code, (load().lspg_last_error() or b"").decode("utf-8", "replace"))
+
+
+def check_h(code: int) -> None:
+    if code != 0:
+        raise LspgError(code, (load().lsph_last_error() or b"").decode("utf-8", "replace"))

@@ -1,7 +1,7 @@
 """Compile the CUDA extension in-tree for sm_100a (nvcc cross-compiles without a GPU).
 
 ``python -m livespeechportraits_b200.build`` or ``build_library()`` produces
-``livespeechportraits_b200/liblspg.so`` - a plain C-ABI shared library (include/lspg.h), statically linked
+``livespeechportraits_b200/liblspg.so`` - a plain C-ABI shared library (include/lspg.h, include/lsph.h), statically linked
 against cudart and without a link-time dependency on libcuda (the one driver entry point it needs,
 cuTensorMapEncodeTiled, is resolved at run time), so it also loads on a machine without a driver.
 """
@@ -15,8 +15,9 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "liblspg.so")
-SOURCES = ["lspg.cu"]
-HEADERS = ["conv_umma.cuh", "ptx.cuh", "aux_kernels.cuh", "raster.cuh", os.path.join("..", "..", "include", "lspg.h")]
+SOURCES = ["lspg.cu", "lsph.cu"]
+HEADERS = ["conv_umma.cuh", "ptx.cuh", "aux_kernels.cuh", "raster.cuh", os.path.join("..", "..", "include", "lspg.h"),
+           os.path.join("..", "..", "include", "lsph.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
