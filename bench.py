@@ -638,6 +638,33 @@ def main():
         except Exception as exc:      # noqa: BLE001
             side["error"] = f"{type(exc).__name__}: {exc}"
         extras["other_configs"] = side
+        # N4: the Audio2Headpose loop of the same clip (687 audio rows -> 672 frames) in one persistent kernel,
+        # next to the reference's loop (oracle port of models/audio2headpose_model.py:169-187) timed on the host CPU
+        try:
+            from livespeechportraits_b200.headpose import HeadposeGenerator
+            from oracle import a2h_oracle as AO
+            hopt = AO.default_opt()
+            hsd = AO.make_state_dict(hopt, "B", 1)
+            audio = AO.make_audio_feats(CLIP_FRAMES + hopt.frame_future, hopt, 2)
+            noise = AO.reference_noise(CLIP_FRAMES, 12, 1, seed=0)
+            pre = np.zeros(12, np.float32)
+            gen = HeadposeGenerator(hopt, hsd, device=dev)
+            a_d, n_d, p_d = torch.from_numpy(audio).to(dev), torch.from_numpy(noise).to(dev), torch.from_numpy(pre).to(dev)
+            ms8 = timed_ms(lambda: gen.generate(a_d, p_d, n_d, 0.3, cluster=8), 3, 1)
+            ms1 = timed_ms(lambda: gen.generate(a_d, p_d, n_d, 0.3, cluster=1), 2, 1)
+            got = gen.generate(a_d, p_d, n_d, 0.3, cluster=8).cpu().numpy()
+            t0 = time.perf_counter()
+            ref = AO.generate_sequences(hsd, audio[:24 + hopt.frame_future], pre, noise[:24], hopt, 0.3)
+            cpu_ms = (time.perf_counter() - t0) / 24 * 1e3
+            extras["headpose_loop"] = {
+                "frames": CLIP_FRAMES, "ms_per_clip": ms8, "frames_per_s": CLIP_FRAMES / ms8 * 1e3, "ms_per_clip_single_cta": ms1,
+                "us_per_frame": ms8 / (CLIP_FRAMES + 254) * 1e3, "max_abs_err_vs_oracle_first_24_frames": float(np.abs(got[:24] - ref).max()),
+                "cpu_reference_ms_per_frame": cpu_ms, "cpu_reference_s_per_clip_extrapolated": cpu_ms * CLIP_FRAMES / 1e3,
+                "api": "livespeechportraits_b200.headpose.HeadposeGenerator.generate (lsph_generate): incremental WaveNet + "
+                       "Sample_GMM in one persistent 8-CTA cluster kernel; replaces models/audio2headpose_model.py:169-187"}
+            del gen
+        except Exception as exc:      # noqa: BLE001
+            extras["headpose_loop"] = {"unavailable": f"{type(exc).__name__}: {exc}"}
         try:
             extras["library_baseline"] = library_baseline(VARIANT, B, H, W)
         except Exception as exc:      # noqa: BLE001

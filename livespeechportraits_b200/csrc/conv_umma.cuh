@@ -525,14 +525,36 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
 
   if (warp == 0) {
     // ===================================================================== TMA producer
+    // Weights are never written by a kernel, so the weight tiles of this CTA's first K blocks (a whole ring of them) are
+    // requested BEFORE the programmatic-dependency wait: they stream from HBM/L2 while the previous layer is still
+    // finishing.  At batch 1 the layers below 16x16 are one tile of 4-9 K blocks per CTA - their whole weight share.
+    int pre = 0;
+    if (static_cast<int>(blockIdx.x) < p.total_tiles) {
+      const TileCoord tc = decode_tile(p, blockIdx.x);
+      const int kb0 = tc.split * p.split_len;
+      const int kb1 = (kb0 + p.split_len < num_kb) ? kb0 + p.split_len : num_kb;
+      pre = (kb1 - kb0 < Cfg::kStages) ? kb1 - kb0 : Cfg::kStages;
+      if (ptx::elect_one()) {
+        for (int i = 0; i < pre; ++i) {          // first use of stages 0..pre-1: no empty-barrier wait needed
+          uint8_t* st = smem + i * Cfg::kStage;
+          ptx::mbar_expect_tx(&full_bar[i], Cfg::kStage);
+#pragma unroll
+          for (int l = 0; l < NL; ++l)
+            ptx::tma_load_3d(&p.w, &full_bar[i], st + NL * kATile + l * Cfg::kBTile, (kb0 + i) * kChunk, tc.nt * BN,
+                             l * p.n_phases + tc.z);
+        }
+      }
+      __syncwarp();
+    }
     ptx::pdl_wait();                // activations are written by the previous kernel
     int stage = 0;
     uint32_t phase = 0;
+    int issued = 0;                 // K blocks issued so far by this CTA (the first `pre` already have their weight tiles)
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
       const TileCoord tc = decode_tile(p, t);
       const int kb0 = tc.split * p.split_len;
       const int kb1 = (kb0 + p.split_len < num_kb) ? kb0 + p.split_len : num_kb;
-      for (int kb = kb0; kb < kb1; ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb, ++issued) {
         const int tap = kb / kb_per_tap;
         const int rem = kb - tap * kb_per_tap;
         const int s = (rem < p.chunks[0]) ? 0 : 1;
@@ -540,15 +562,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
         const int amap = p.tap_map[tc.z][tap];
         const int xx = tc.x0 + p.tap_dx[tc.z][tap];
         const int yy = tc.y0 + p.tap_dy[tc.z][tap];
-        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+        const bool early = issued < pre;
+        if (!early) ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
         if (ptx::elect_one()) {
           uint8_t* st = smem + stage * Cfg::kStage;
-          ptx::mbar_expect_tx(&full_bar[stage], Cfg::kStage);
+          if (!early) ptx::mbar_expect_tx(&full_bar[stage], Cfg::kStage);
 #pragma unroll
           for (int l = 0; l < NL; ++l) {
             ptx::tma_load_5d(&p.a[amap + s], &full_bar[stage], st + l * kATile, c * kChunk, xx, yy, tc.n0, l);
-            ptx::tma_load_3d(&p.w, &full_bar[stage], st + NL * kATile + l * Cfg::kBTile, kb * kChunk, tc.nt * BN,
-                             l * p.n_phases + tc.z);
+            if (!early)
+              ptx::tma_load_3d(&p.w, &full_bar[stage], st + NL * kATile + l * Cfg::kBTile, kb * kChunk, tc.nt * BN,
+                               l * p.n_phases + tc.z);
           }
         }
         __syncwarp();
@@ -971,7 +995,7 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) conv_pair_kernel(const __grid
 
   if (warp == 0) {
     // ===================================================================== TMA producer (both CTAs)
-    ptx::pdl_wait();
+    // (the dependency wait comes after the first weight requests: weights are never written by a kernel)
     int ia = 0, ib = 0;
     uint32_t pha = 0, phb = 0;
     int a_tile = blockIdx.x, a_ci = 0, a_lt = 0;
@@ -1025,6 +1049,22 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) conv_pair_kernel(const __grid
         __syncwarp();
       }
     }
+    // streaming layers: the first ring of weight tiles (first use of every stage: no empty-barrier wait) goes out early too
+    int pre = 0, b_items = 0;
+    if (!p.b_resident && static_cast<int>(blockIdx.x) < p.total_tiles) {
+      const TileCoord tc = decode_tile(p, blockIdx.x);
+      const int n_items = kb_per_tap * p.n_taps;
+      pre = n_items < Cfg::kBStages ? n_items : Cfg::kBStages;
+      if (ptx::elect_one()) {
+        for (int i = 0; i < pre; ++i) {
+          const int ci = i / p.n_taps, tap = i - ci * p.n_taps;
+          if (leader_cta) ptx::mbar_expect_tx(&bfull_bar[i], 2 * Cfg::kBStage);
+          load_b(b_ring + i * Cfg::kBStage, &bfull_bar[i], ci, tc.nt, tap, tc.z);
+        }
+      }
+      __syncwarp();
+    }
+    ptx::pdl_wait();                // activations are written by the previous kernel
     issue_a();
     const int a_after = (p.n_taps > 2) ? 2 : p.n_taps - 1;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
@@ -1035,11 +1075,15 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) conv_pair_kernel(const __grid
             if (tap == a_after) issue_a();
             continue;
           }
-          ptx::mbar_wait(&bempty_bar[ib], phb ^ 1);
-          if (ptx::elect_one()) {
-            uint8_t* st = b_ring + ib * Cfg::kBStage;
-            if (leader_cta) ptx::mbar_expect_tx(&bfull_bar[ib], 2 * Cfg::kBStage);    // both CTAs' shares
-            load_b(st, &bfull_bar[ib], ci, tc.nt, tap, tc.z);
+          const bool early = b_items < pre;
+          ++b_items;
+          if (!early) {
+            ptx::mbar_wait(&bempty_bar[ib], phb ^ 1);
+            if (ptx::elect_one()) {
+              uint8_t* st = b_ring + ib * Cfg::kBStage;
+              if (leader_cta) ptx::mbar_expect_tx(&bfull_bar[ib], 2 * Cfg::kBStage);    // both CTAs' shares
+              load_b(st, &bfull_bar[ib], ci, tc.nt, tap, tc.z);
+            }
           }
           __syncwarp();
           if (++ib == Cfg::kBStages) { ib = 0; phb ^= 1; }
