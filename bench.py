@@ -326,11 +326,11 @@ def main():
 
     def pool_seed(r: int, i: int) -> int:
         return 100 + r * 16 + i
-    fm_pool, cand_cpu = [], None
+    fm_pool = []
     for i in range(pool):
-        fm, cd = O.make_inputs(B, H, W, seed=pool_seed(rank, i))
+        fm, _ = O.make_inputs(B, H, W, seed=pool_seed(rank, i))
         fm_pool.append(fm.cuda())
-        cand_cpu = cd[:1]
+    cand_cpu = O.make_inputs(1, H, W, seed=99)[1][:1].contiguous()     # ONE candidate set for every frame of every rank (demo.py:95,266)
     cand = cand_cpu.cuda()
     flops_step = net.flops_per_frame(H, W) * B
 
@@ -376,8 +376,9 @@ def main():
         # into the clip buffer, the frames travel to every rank (copy engines over symmetric memory, or NCCL all-gather).
         sr = ShardedRenderer(lambda fm_, out_: net.render(fm_, cand, out=out_), chunk=B, gather=args.gather)
         local_fm = torch.cat([fm_pool[i % pool] for i in range(K)], 0)                 # this rank's block: K*B frames
-        warm_fm = local_fm[: Wm * B]
-        sr.render(Wm * B * world, warm_fm)
+        wm_c = min(Wm, K)
+        warm_fm = local_fm[: wm_c * B]
+        sr.render(wm_c * B * world, warm_fm)
         barrier()
         if rank == 0:
             sampler.start()
@@ -529,7 +530,7 @@ def main():
     if world > 1 and not args.no_extras:
         # uint8 frames through the same entry point (a quarter of the bytes), and the exact-size clip of configs[3] if asked
         sr8 = ShardedRenderer(lambda fm_, out_: net.render_image(fm_, cand, out=out_), chunk=B, uint8=True, gather=args.gather)
-        sr8.render(Wm * B * world, local_fm[: Wm * B])
+        sr8.render(min(Wm, K) * B * world, local_fm[: min(Wm, K) * B])
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()

@@ -1173,7 +1173,7 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) conv_pair_kernel(const __grid
 }
 
 // ====================================================================================================
-// Split-K finisher: out = epilogue( sum_s partial[s] ).  One thread = one pixel x 8 channels.
+// Split-K finisher: out = epilogue( sum_s partial[s] ).
 // Memory-bound and tiny (the layers that use split-K have at most a few hundred output pixels per image).
 // ====================================================================================================
 struct ReduceParams {
@@ -1189,10 +1189,13 @@ struct ReduceParams {
   int32_t batch, hs, ws, up, channels, relu, has_res, nl;
 };
 
-__global__ void splitk_reduce_kernel(const ReduceParams p) {
+// One thread = one pixel x 4 channels.  The layers that use split-K are latency bound (a few hundred output pixels, 8-36
+// splits): what matters is how many dependent trips to L2 the sum takes, so up to 16 splits are in flight per trip
+// (round 1 summed 4 per trip over 8-channel groups: 6 dependent trips for 18 splits, as long as the conv itself at batch 1).
+__global__ void __launch_bounds__(128) splitk_reduce_kernel(const ReduceParams p) {
   ptx::pdl_wait();
   ptx::pdl_launch_dependents();
-  const int groups = p.bn >> 3;
+  const int groups = p.bn >> 2;
   const long long total = static_cast<long long>(p.tiles_per_split) * kTileM * groups;
   for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < total;
        e += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -1214,61 +1217,54 @@ __global__ void splitk_reduce_kernel(const ReduceParams p) {
     const int n = (tn << (7 - p.tw_log2 - p.th_log2)) + nb;
     const int y = (ty << p.th_log2) + th, x = (tx << p.tw_log2) + tw;
     if (n >= p.batch || y >= p.hs || x >= p.ws) continue;
-    float acc[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
     const size_t split_stride = static_cast<size_t>(p.tiles_per_split) * kTileM * p.bn;      // floats between splits
-    const float* src0 = p.partial + (static_cast<size_t>(tile) * kTileM + row) * p.bn + g * 8;
+    const float* src0 = p.partial + (static_cast<size_t>(tile) * kTileM + row) * p.bn + g * 4;
     int s = 0;
-    for (; s + 4 <= p.n_split; s += 4) {       // four splits per trip: eight independent 16-byte loads in flight
-      float4 v[8];
+    for (; s + 16 <= p.n_split; s += 16) {     // sixteen independent 16-byte loads in flight
+      float4 v[16];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float4* src = reinterpret_cast<const float4*>(src0 + (s + u) * split_stride);
-        v[2 * u] = src[0];
-        v[2 * u + 1] = src[1];
-      }
+      for (int u = 0; u < 16; ++u) v[u] = *reinterpret_cast<const float4*>(src0 + (s + u) * split_stride);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {            // summation order stays s = 0, 1, 2, ... (deterministic)
-        acc[0] += v[2 * u].x; acc[1] += v[2 * u].y; acc[2] += v[2 * u].z; acc[3] += v[2 * u].w;
-        acc[4] += v[2 * u + 1].x; acc[5] += v[2 * u + 1].y; acc[6] += v[2 * u + 1].z; acc[7] += v[2 * u + 1].w;
+      for (int u = 0; u < 16; ++u) {           // summation order stays s = 0, 1, 2, ... (deterministic)
+        acc[0] += v[u].x; acc[1] += v[u].y; acc[2] += v[u].z; acc[3] += v[u].w;
       }
+    }
+    for (; s + 4 <= p.n_split; s += 4) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const float4*>(src0 + (s + u) * split_stride);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { acc[0] += v[u].x; acc[1] += v[u].y; acc[2] += v[u].z; acc[3] += v[u].w; }
     }
     for (; s < p.n_split; ++s) {
-      const float4* src = reinterpret_cast<const float4*>(src0 + s * split_stride);
-      const float4 a = src[0], b = src[1];
+      const float4 a = *reinterpret_cast<const float4*>(src0 + s * split_stride);
       acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
-      acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
     }
-    const int ch = nt * p.bn + g * 8;
+    const int ch = nt * p.bn + g * 4;
     const int oh = p.up ? 2 * p.hs : p.hs, ow = p.up ? 2 * p.ws : p.ws;
     const int oy = p.up ? 2 * y + (z >> 1) : y, ox = p.up ? 2 * x + (z & 1) : x;
     const size_t off = ((static_cast<size_t>(n) * oh + oy) * ow + ox) * p.channels + ch;
-    float yv[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) yv[i] = fmaf(acc[i], p.scale[ch + i], p.shift[ch + i]);
+    const float4 sc = *reinterpret_cast<const float4*>(p.scale + ch), sh = *reinterpret_cast<const float4*>(p.shift + ch);
+    float yv[4] = {fmaf(acc[0], sc.x, sh.x), fmaf(acc[1], sc.y, sh.y), fmaf(acc[2], sc.z, sh.z), fmaf(acc[3], sc.w, sh.w)};
     if (p.has_res) {
       for (int l = 0; l < p.nl; ++l) {
-        const uint4 r = *reinterpret_cast<const uint4*>(p.res + l * p.res_limb_stride + off);
-        const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { yv[2 * i] += bf16_lo(rr[i]); yv[2 * i + 1] += bf16_hi(rr[i]); }
+        const uint2 r = *reinterpret_cast<const uint2*>(p.res + l * p.res_limb_stride + off);
+        yv[0] += bf16_lo(r.x); yv[1] += bf16_hi(r.x); yv[2] += bf16_lo(r.y); yv[3] += bf16_hi(r.y);
       }
     }
     if (p.relu) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) yv[i] = fmaxf(yv[i], 0.f);
+      for (int i = 0; i < 4; ++i) yv[i] = fmaxf(yv[i], 0.f);
     }
-    uint4 o;
+    uint2 o;
     o.x = pack_bf16x2(yv[0], yv[1]); o.y = pack_bf16x2(yv[2], yv[3]);
-    o.z = pack_bf16x2(yv[4], yv[5]); o.w = pack_bf16x2(yv[6], yv[7]);
-    *reinterpret_cast<uint4*>(p.out + off) = o;
+    *reinterpret_cast<uint2*>(p.out + off) = o;
     if (p.nl == 2) {
-      const uint32_t oo[4] = {o.x, o.y, o.z, o.w};
-      uint32_t lo[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) lo[i] = pack_bf16x2(yv[2 * i] - bf16_lo(oo[i]), yv[2 * i + 1] - bf16_hi(oo[i]));
-      *reinterpret_cast<uint4*>(p.out + p.out_limb_stride + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      uint2 lo;
+      lo.x = pack_bf16x2(yv[0] - bf16_lo(o.x), yv[1] - bf16_hi(o.x));
+      lo.y = pack_bf16x2(yv[2] - bf16_lo(o.y), yv[3] - bf16_hi(o.y));
+      *reinterpret_cast<uint2*>(p.out + p.out_limb_stride + off) = lo;
     }
   }
 }

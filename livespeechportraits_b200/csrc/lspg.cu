@@ -787,7 +787,7 @@ int build_plan(lspg_ctx* h, Plan* P, int B, int H, int W, int mode, void* worksp
       r.n_phases = L.n_phases; r.tiles_x = p.tiles_x; r.tiles_y = p.tiles_y; r.tw_log2 = p.tw_log2; r.th_log2 = p.th_log2;
       r.bn = g.bn; r.batch = B; r.hs = Hs; r.ws = Ws; r.up = (L.kind == K_UP) ? 1 : 0; r.channels = L.cout_pad;
       r.relu = L.relu; r.has_res = L.res >= 0 ? 1 : 0; r.nl = NL;
-      const long long work = static_cast<long long>(g.tiles_per_split) * kTileM * (g.bn / 8);
+      const long long work = static_cast<long long>(g.tiles_per_split) * kTileM * (g.bn / 4);   // one thread per pixel x 4 channels
       pl.red_blocks = static_cast<int>(std::min<long long>((work + 127) / 128, 8LL * h->num_sms));
     }
     P->layers.push_back(pl);
