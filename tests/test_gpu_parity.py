@@ -14,7 +14,7 @@ from oracle import f2f_oracle as O
 pytestmark = pytest.mark.gpu
 TOL = 1e-3
 GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
-                if not os.path.basename(p).startswith("raster_"))      # raster_*: tests/test_raster_oracle.py
+                if not os.path.basename(p).startswith(("raster_", "a2h_")))      # raster_*: tests/test_raster_oracle.py
 
 
 def opt(size):

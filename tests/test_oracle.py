@@ -10,7 +10,7 @@ import torch
 from oracle import f2f_oracle as O
 
 GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
-                if not os.path.basename(p).startswith("raster_"))      # raster_*: tests/test_raster_oracle.py
+                if not os.path.basename(p).startswith(("raster_", "a2h_")))      # raster_*: tests/test_raster_oracle.py
 
 
 def test_key_grammar_and_parameter_counts():
