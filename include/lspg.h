@@ -134,7 +134,9 @@ typedef struct lspg_layer_geo {
   int m_tiles, n_tiles, n_phases;
   int n_split, split_len, k_items;   /* split-K: K loop of k_items cut into n_split ranges of split_len */
   int ctas;              /* CTAs launched = min(tiles * n_split, SMs), even for the pair kernel */
-  int64_t partial_bytes; /* fp32 split-K partials this layer needs in the scratch region */
+  int64_t partial_bytes; /* fp32 split-K partials this layer needs in the scratch region (0 for a cluster split) */
+  int cluster_split;     /* > 0: the n_split CTAs of a tile are one thread-block cluster and reduce through distributed shared
+                            memory (no finisher launch); then n_split == cluster_split in {2, 4, 8} */
 } lspg_layer_geo;
 int lspg_debug_layer_geo(lspg_handle h, int layer, int batch, int height, int width, lspg_layer_geo* out);
 

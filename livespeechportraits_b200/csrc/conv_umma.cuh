@@ -87,6 +87,8 @@ struct alignas(64) ConvParams {
   // tile index = split * tiles_per_split + tile.  Each CTA writes its raw fp32 accumulator tile to
   // partial[tile_index][128][BN]; splitk_reduce_kernel sums the splits and applies the epilogue.
   int32_t n_split, tiles_per_split;
+  int32_t cluster_split;     // 1: the n_split CTAs of a tile form a thread-block cluster and reduce their partials through
+                             // distributed shared memory (CSP kernel variants); 0: partials go to `partial` + finisher kernel
   int32_t n_tiles;           // Cout_pad / BN
   int32_t tiles_x, tiles_y, tiles_n;
   int32_t n_phases;
@@ -114,12 +116,16 @@ struct alignas(64) ConvParams {
   CUtensorMap out[4];        // output views per phase, dims {C, X, Y, N, limb}
 };
 
-template <int BN, int NL, bool TAIL>
+// CSP ("cluster split"): split-K inside a thread-block cluster.  The n_split (2, 4 or 8) CTAs that share an output tile are
+// one cluster; every CTA owns 128 / n_split rows of the tile and receives those rows of every CTA's fp32 partial in a
+// staging buffer of its own shared memory (128 x BN floats in total), sums them in split order and applies the epilogue.
+// No partials in global memory and no finisher launch (at batch 1 the finishers were 46 of 123 launches).
+template <int BN, int NL, bool TAIL, bool CSP = false>
 struct ConvCfg {
   static constexpr int kBTile = BN * 128;
   static constexpr int kStage = NL * (kATile + kBTile);
-  static constexpr int kNumStg = 0;                                  // (no smem staging: the epilogue writes global memory directly)
-  static constexpr int kStgBytes = kNumStg * NL * kATile;
+  static constexpr int kNumStg = 0;                                  // (no smem staging of results: the epilogue writes global memory directly)
+  static constexpr int kStgBytes = CSP ? kTileM * BN * 4 : 0;        // cluster split-K: partial rows from the cluster's CTAs
   static constexpr int kAux = 3072;                                  // 2 x (scale, shift) + barriers + tmem ptr
   static constexpr int kAvail = kSmemBudget - 1024 /*alignment slack*/ - kStgBytes - kAux;
   static constexpr int kStagesRaw = kAvail / kStage;
@@ -211,10 +217,10 @@ struct StgCfg {
 // EW = number of epilogue warps (4 or 8).  A warp may read TMEM lane quarter (warp % 4); with EW = 8 two warps share a
 // quarter and split the columns in interleaved 32-column pieces, which doubles the loads/stores in flight and the issue
 // slots of the epilogue (the 64-channel layers were epilogue-bound with 4 warps: 6.2k cycles vs 3.5k of MMAs per tile).
-template <int BN, int NL, bool TAIL, int NSTG, bool STACK, bool PAIR = false, int EW = 4, int NACC = 2>
-__device__ __forceinline__ void epilogue_warps(const ConvParams& p, uint8_t* /*stg_base*/, float* s_scale0, float* /*unused*/,
+template <int BN, int NL, bool TAIL, int NSTG, bool STACK, bool PAIR = false, int EW = 4, int NACC = 2, bool CSP = false>
+__device__ __forceinline__ void epilogue_warps(const ConvParams& p, uint8_t* stg_base, float* s_scale0, float* /*unused*/,
                                                uint64_t* tfull_bar, uint64_t* tempty_bar, uint64_t* stg_bar,
-                                               uint32_t tmem_base, int warp, int lane) {
+                                               uint32_t tmem_base, int warp, int lane, int t0, int tstep) {
   static_assert(EW == 4 || EW == 8, "4 or 8 epilogue warps");
   static_assert(!(TAIL && EW != 4), "the tail epilogue uses 4 warps");
   constexpr int kEpi = EW * 32;
@@ -277,16 +283,16 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, uint8_t* /*s
         ptx::ldg256_nc(rr + l * p.res_limb_stride + h2 * 16, rs[l][2 * h2], rs[l][2 * h2 + 1]);
   };
   int lt = 0;
-  TileCoord tc_next = decode_tile(p, blockIdx.x);
-  if (static_cast<int>(blockIdx.x) < p.total_tiles) {
+  TileCoord tc_next = decode_tile(p, t0);
+  if (t0 < p.total_tiles) {
     if (use_res) load_res(tc_next, grp);
   }
-  for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++lt) {
+  for (int t = t0; t < p.total_tiles; t += tstep, ++lt) {
     const TileCoord tc = tc_next;
     if (leader) trace_tile(p, lt, 3);
     const bool split_mode = !TAIL && p.n_split > 1;
     if (tc.nt != cur_nt) fetch_affine(tc.nt);
-    const int t_next = t + gridDim.x;
+    const int t_next = t + tstep;
     if (t_next < p.total_tiles) tc_next = decode_tile(p, t_next);
 
     constexpr int kAccCols = STACK ? 2 * BN : BN;
@@ -350,7 +356,32 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, uint8_t* /*s
       }
     } else {
       constexpr int kPieces = BN / 32;             // 32-column pieces of the tile; this warp takes grp, grp+kGroups, ...
-      if (split_mode) {
+      if (split_mode && CSP) {
+        // ---- cluster split-K: this thread's fp32 accumulator row goes to the CTA that owns the row (distributed shared
+        // memory), into the slot of this CTA's rank; cluster_split_finish() sums the slots after the cluster barrier.
+        const int rpo = kTileM / p.n_split;                      // rows per owner
+        const uint32_t owner = static_cast<uint32_t>(row / rpo);
+        const int lr = row - static_cast<int>(owner) * rpo;
+        const uint32_t my_rank = ptx::cluster_ctarank();
+        const uint32_t dst = ptx::mapa_u32(ptx::smem_u32(stg_base) + ((my_rank * rpo + lr) * BN) * 4u, owner);
+#pragma unroll 1
+        for (int c32 = grp; c32 < kPieces; c32 += kGroups) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32(t_acc + c32 * 32, v);
+          if constexpr (STACK) {
+            uint32_t v2[32];
+            ptx::tmem_ld_32x32(t_acc + BN + c32 * 32, v2);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
+          }
+          ptx::tmem_ld_wait();
+          if (c32 + kGroups >= kPieces) release_tmem();
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            ptx::st_cluster_v4(dst + (c32 * 32 + e * 4) * 4u, v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+        }
+      } else if (split_mode) {
         // ---- split-K partial: raw fp32 accumulator rows -> partial[t][row][BN]
         float* dst = p.partial + (static_cast<size_t>(t) * kTileM + row) * BN;
 #pragma unroll 1
@@ -472,9 +503,82 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, uint8_t* /*s
   }
 }
 
-template <int BN, int NL, bool TAIL>
+// Cluster split-K, second half (after the cluster barrier): the epilogue warps of every CTA sum the n_split partial slots of
+// the 128 / n_split tile rows this CTA owns (in split order: deterministic) and apply the layer's epilogue - folded BatchNorm,
+// residual, ReLU, bf16 hi/lo split - writing the NHWC output directly.  One thread = one pixel x 4 channels per trip.
+template <int BN, int NL, int EW>
+__device__ __forceinline__ void cluster_split_finish(const ConvParams& p, const uint8_t* stg_base, int t) {
+  constexpr int kEpi = EW * 32;
+  const int etid = threadIdx.x - 64;
+  const TileCoord tc = decode_tile(p, t);
+  const int cs = p.n_split, rpo = kTileM / cs;
+  const int rank = static_cast<int>(ptx::cluster_ctarank());
+  const float* stg = reinterpret_cast<const float*>(stg_base);
+  constexpr int kGroups4 = BN / 4;
+  for (int e = etid; e < rpo * kGroups4; e += kEpi) {
+    const int g = e % kGroups4, lr = e / kGroups4;
+    const int row = rank * rpo + lr;
+    const int tw_ = row & ((1 << p.tw_log2) - 1);
+    const int th_ = (row >> p.tw_log2) & ((1 << p.th_log2) - 1);
+    const int nb_ = row >> (p.tw_log2 + p.th_log2);
+    const int n = tc.n0 + nb_, y = tc.y0 + th_, x = tc.x0 + tw_;
+    if (n >= p.batch || y >= p.hs || x >= p.ws) continue;
+    float4 acc = *reinterpret_cast<const float4*>(stg + (static_cast<size_t>(lr) * BN + g * 4));
+    for (int sp = 1; sp < cs; ++sp) {
+      const float4 a = *reinterpret_cast<const float4*>(stg + (static_cast<size_t>(sp * rpo + lr) * BN + g * 4));
+      acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+    }
+    const int ch = tc.nt * BN + g * 4;
+    const float4 sc = *reinterpret_cast<const float4*>(p.scale + ch), sh = *reinterpret_cast<const float4*>(p.shift + ch);
+    float yv[4] = {fmaf(acc.x, sc.x, sh.x), fmaf(acc.y, sc.y, sh.y), fmaf(acc.z, sc.z, sh.z), fmaf(acc.w, sc.w, sh.w)};
+    if (p.has_res) {
+      const __nv_bfloat16* rr = p.res_ptr + ((static_cast<size_t>(n) * p.hs + y) * p.ws + x) * p.res_channels + ch;
+#pragma unroll
+      for (int l = 0; l < NL; ++l) {
+        const uint2 r = *reinterpret_cast<const uint2*>(rr + l * p.res_limb_stride);
+        yv[0] += bf16_lo(r.x); yv[1] += bf16_hi(r.x); yv[2] += bf16_lo(r.y); yv[3] += bf16_hi(r.y);
+      }
+    }
+    if (p.relu) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) yv[i] = fmaxf(yv[i], 0.f);
+    }
+    const int oh = p.out_up ? 2 * p.hs : p.hs, ow = p.out_up ? 2 * p.ws : p.ws;
+    const int oy = p.out_up ? 2 * y + (tc.z >> 1) : y, ox = p.out_up ? 2 * x + (tc.z & 1) : x;
+    __nv_bfloat16* out = p.out_ptr + ((static_cast<size_t>(n) * oh + oy) * ow + ox) * p.out_channels + ch;
+    uint2 o;
+    o.x = pack_bf16x2(yv[0], yv[1]); o.y = pack_bf16x2(yv[2], yv[3]);
+    *reinterpret_cast<uint2*>(out) = o;
+    if (NL == 2) {
+      uint2 lo;
+      lo.x = pack_bf16x2(yv[0] - bf16_lo(o.x), yv[1] - bf16_hi(o.x));
+      lo.y = pack_bf16x2(yv[2] - bf16_lo(o.y), yv[3] - bf16_hi(o.y));
+      *reinterpret_cast<uint2*>(out + p.out_limb_stride) = lo;
+    }
+  }
+}
+
+// Tile walk of a CTA: persistent (blockIdx.x, +gridDim.x, ...) or, in a cluster split-K launch, exactly one tile whose
+// split index is the CTA's rank in its cluster (grid = tiles x n_split, clusters of n_split consecutive CTAs).
+template <bool CSP>
+__device__ __forceinline__ void tile_walk(const ConvParams& p, int& t0, int& tstep) {
+  if constexpr (CSP) {
+    const int cs = p.n_split;
+    const int tile = static_cast<int>(blockIdx.x) / cs, split = static_cast<int>(blockIdx.x) - tile * cs;
+    t0 = split * p.tiles_per_split + tile;
+    tstep = p.total_tiles;                  // one tile per CTA
+  } else {
+    t0 = static_cast<int>(blockIdx.x);
+    tstep = static_cast<int>(gridDim.x);
+  }
+}
+
+template <int BN, int NL, bool TAIL, bool CSP = false>
 __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_constant__ ConvParams p) {
-  using Cfg = ConvCfg<BN, NL, TAIL>;
+  using Cfg = ConvCfg<BN, NL, TAIL, CSP>;
+  static_assert(!(CSP && TAIL), "the tail conv never splits K");
+  int t0, tstep;
+  tile_walk<CSP>(p, t0, tstep);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stg_base = smem + Cfg::kStages * Cfg::kStage;
@@ -515,6 +619,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if constexpr (CSP) ptx::cluster_sync();   // every CTA of the cluster is running before anyone writes into its shared memory
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   ptx::pdl_launch_dependents();   // the next kernel may start its prologue; it waits (pdl_wait) before touching our output
@@ -529,8 +634,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     // requested BEFORE the programmatic-dependency wait: they stream from HBM/L2 while the previous layer is still
     // finishing.  At batch 1 the layers below 16x16 are one tile of 4-9 K blocks per CTA - their whole weight share.
     int pre = 0;
-    if (static_cast<int>(blockIdx.x) < p.total_tiles) {
-      const TileCoord tc = decode_tile(p, blockIdx.x);
+    if (t0 < p.total_tiles) {
+      const TileCoord tc = decode_tile(p, t0);
       const int kb0 = tc.split * p.split_len;
       const int kb1 = (kb0 + p.split_len < num_kb) ? kb0 + p.split_len : num_kb;
       pre = (kb1 - kb0 < Cfg::kStages) ? kb1 - kb0 : Cfg::kStages;
@@ -550,7 +655,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     int stage = 0;
     uint32_t phase = 0;
     int issued = 0;                 // K blocks issued so far by this CTA (the first `pre` already have their weight tiles)
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+    for (int t = t0; t < p.total_tiles; t += tstep) {
       const TileCoord tc = decode_tile(p, t);
       const int kb0 = tc.split * p.split_len;
       const int kb1 = (kb0 + p.split_len < num_kb) ? kb0 + p.split_len : num_kb;
@@ -585,7 +690,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+    for (int t = t0; t < p.total_tiles; t += tstep) {
       ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BN;
@@ -621,7 +726,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
-    epilogue_warps<BN, NL, TAIL, Cfg::kNumStg, false>(p, stg_base, s_scale, s_shift, tfull_bar, tempty_bar, stg_bar, tmem_base, warp, lane);
+    epilogue_warps<BN, NL, TAIL, Cfg::kNumStg, false, false, 4, 2, CSP>(p, stg_base, s_scale, s_shift, tfull_bar, tempty_bar, stg_bar,
+                                                                         tmem_base, warp, lane, t0, tstep);
+  }
+  if constexpr (CSP) {
+    // every CTA of the cluster has written its partial rows into the owners' staging buffers
+    ptx::cluster_sync();
+    if (warp >= 2) cluster_split_finish<BN, NL, 4>(p, stg_base, t0);
   }
 
   ptx::tc_fence_before();
@@ -647,7 +758,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
 constexpr int kPatchSlot = 23 * 1024;           // >= 10*18*128 = 23040 bytes
 constexpr int kPatchStride = 23 * 1024;         // distance between patch buffers (1024-byte aligned)
 
-template <int BN, int NL, bool TAIL>
+template <int BN, int NL, bool TAIL, bool CSP = false>
 struct PatchCfg {
   static constexpr int kBTile = BN * 128;
   // taps per B stage: one mbarrier round trip per stage costs the MMA-issuing thread a few hundred cycles, so a
@@ -661,7 +772,7 @@ struct PatchCfg {
   // one is requested a full chunk ahead); everything else goes to B stages.
   static constexpr int kAStages = 2;
   static constexpr int kNumStg = 0;
-  static constexpr int kStgBytes = kNumStg * NL * kATile;
+  static constexpr int kStgBytes = CSP ? kTileM * BN * 4 : 0;        // cluster split-K staging (see ConvCfg)
   static constexpr int kAux = 3072;
   static constexpr int kAvail = kSmemBudget - 1024 - kStgBytes - kAux - kAStages * kAStage;
   static constexpr int kBStagesRaw = kAvail / kBStage;
@@ -690,9 +801,12 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_strided(uint32_t smem_addr, 
 // to both (cp.async.bulk.tensor ... .multicast::cluster), halving the L2->SM weight traffic that clock64 traces showed
 // to be the limiter (~30-36 B/clk/SM of weight tiles, every SM asking L2 for the same lines).  A stage is refilled
 // only after BOTH CTAs' MMAs released it (tcgen05.commit ... .multicast::cluster onto both bempty barriers).
-template <int BN, int NL, bool TAIL, int CL, int EW>
+template <int BN, int NL, bool TAIL, int CL, int EW, bool CSP = false>
 __global__ void __launch_bounds__(64 + EW * 32, 1) conv_patch_kernel(const __grid_constant__ ConvParams p) {
-  using Cfg = PatchCfg<BN, NL, TAIL>;
+  using Cfg = PatchCfg<BN, NL, TAIL, CSP>;
+  static_assert(!(CSP && (TAIL || CL != 1)), "cluster split-K: no tail, no B multicast cluster");
+  int t0, tstep;
+  tile_walk<CSP>(p, t0, tstep);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_ring = smem;
@@ -736,7 +850,7 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) conv_patch_kernel(const __gri
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (CL > 1) ptx::cluster_sync();     // peers' barriers are initialised before anyone multicasts into them
+  if (CL > 1 || CSP) ptx::cluster_sync();     // peers' barriers are initialised / peers are running before remote smem is touched
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t crank = (CL > 1) ? ptx::cluster_ctarank() : 0u;
@@ -755,7 +869,7 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) conv_patch_kernel(const __gri
     ptx::pdl_wait();                // activations are written by the previous kernel
     int ia = 0, ib = 0;
     uint32_t pha = 0, phb = 0;
-    int a_tile = blockIdx.x, a_ci = -1;            // cursor of the next A patch to issue (-1: take the tile's first item)
+    int a_tile = t0, a_ci = -1;            // cursor of the next A patch to issue (-1: take the tile's first item)
     auto issue_a = [&]() {
       if (a_tile >= p.total_tiles) return;
       const TileCoord tc = decode_tile(p, a_tile);
@@ -774,13 +888,13 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) conv_patch_kernel(const __gri
       }
       __syncwarp();
       if (++ia == Cfg::kAStages) { ia = 0; pha ^= 1; }
-      if (++a_ci == ci1) { a_ci = -1; a_tile += gridDim.x; }
+      if (++a_ci == ci1) { a_ci = -1; a_tile += tstep; }
     };
     issue_a();
     const int n_groups = (p.n_taps + Cfg::kTPS - 1) / Cfg::kTPS;
     const int a_after_group = (n_groups > 1) ? 1 : 0;
     int lt = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++lt) {
+    for (int t = t0; t < p.total_tiles; t += tstep, ++lt) {
       const TileCoord tc = decode_tile(p, t);
       const int ci0 = tc.split * p.split_len;
       const int ci1 = (ci0 + p.split_len < kb_per_tap) ? ci0 + p.split_len : kb_per_tap;
@@ -832,7 +946,7 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) conv_patch_kernel(const __gri
     const int n_groups = (p.n_taps + Cfg::kTPS - 1) / Cfg::kTPS;
     bool b_ready = false;
     int lt = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++lt) {
+    for (int t = t0; t < p.total_tiles; t += tstep, ++lt) {
       TileCoord tc;
       decode_tile_zs(p, t, tc.z, tc.split);
       ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -887,7 +1001,12 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) conv_patch_kernel(const __gri
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
-    epilogue_warps<BN, NL, TAIL, Cfg::kNumStg, (NL == 2), false, EW>(p, stg_base, s_scale, s_shift, tfull_bar, tempty_bar, stg_bar, tmem_base, warp, lane);
+    epilogue_warps<BN, NL, TAIL, Cfg::kNumStg, (NL == 2), false, EW, 2, CSP>(p, stg_base, s_scale, s_shift, tfull_bar, tempty_bar, stg_bar,
+                                                                              tmem_base, warp, lane, t0, tstep);
+  }
+  if constexpr (CSP) {
+    ptx::cluster_sync();                 // every CTA's partial rows are in their owners' staging buffers
+    if (warp >= 2) cluster_split_finish<BN, NL, EW>(p, stg_base, t0);
   }
 
   ptx::tc_fence_before();
@@ -1159,7 +1278,8 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) conv_pair_kernel(const __grid
       }
     }
   } else {
-    epilogue_warps<BN, NL, false, 0, STK, true, EW, NACC>(p, aux, s_scale, s_shift, tfull_bar, tempty_bar, stg_bar, tmem_base, warp, lane);
+    epilogue_warps<BN, NL, false, 0, STK, true, EW, NACC>(p, aux, s_scale, s_shift, tfull_bar, tempty_bar, stg_bar, tmem_base, warp, lane,
+                                                          static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x));
   }
 
   ptx::tc_fence_before();

@@ -101,6 +101,7 @@ struct PlanLayer {
   bool pair = false;      // conv_pair_kernel (cta_group::2)
   int cluster = 1;        // CTAs per cluster sharing B stages by TMA multicast (patch mode only)
   bool split = false;     // split-K: conv kernel writes fp32 partials, splitk_reduce_kernel finishes
+  int csplit = 0;         // split-K inside a cluster of this many CTAs (no finisher)
   ReduceParams red;
   int red_blocks = 0;
 };
@@ -454,6 +455,7 @@ struct Geo {
   int n_split, split_len;
   size_t partial_bytes;
   bool pair;                   // conv_pair_kernel: cta_group::2 UMMA over a 2-CTA cluster (wide layers)
+  int csplit;                  // > 0: split-K inside a thread-block cluster of this many CTAs (DSMEM reduction, no finisher)
 };
 
 Geo layer_geo(const lspg_ctx* h, const Layer& L, int B, int H, int W) {
@@ -502,7 +504,7 @@ Geo layer_geo(const lspg_ctx* h, const Layer& L, int B, int H, int W) {
   }
   g.n_tiles = L.cout_pad / g.bn;
   g.tiles_per_split = g.m_tiles * g.n_tiles * L.n_phases;
-  g.n_split = 1; g.split_len = g.k_items; g.partial_bytes = 0;
+  g.n_split = 1; g.split_len = g.k_items; g.partial_bytes = 0; g.csplit = 0;
   const int sms = h->num_sms_or_default();
   if (!no_split && !g.pair && L.kind != K_TAIL && g.tiles_per_split * 2 <= sms) {
     const int min_len = g.patch ? 1 : 4;                       // at least 4 K blocks (v1) / 1 chunk of all taps per split
@@ -510,7 +512,20 @@ Geo layer_geo(const lspg_ctx* h, const Layer& L, int B, int H, int W) {
     int max_split = g.k_items / min_len;
     if (max_split < 1) max_split = 1;
     if (want > max_split) want = max_split;
-    if (want > 1) {
+    // Cluster split-K: the 2 / 4 / 8 CTAs of a tile form a cluster, exchange their partial rows through distributed shared
+    // memory and finish the tile themselves - no partials in global memory, no finisher launch.  Needs exactly `cs`
+    // non-empty K ranges and tiles x cs CTAs in one wave.
+    static const bool no_csplit = getenv("LSPG_NO_CLUSTER_SPLIT") != nullptr;
+    if (!no_csplit && want > 1) {
+      for (int cs : {8, 4, 2}) {
+        if (cs > want) continue;
+        const int len = (g.k_items + cs - 1) / cs;
+        if ((g.k_items + len - 1) / len != cs) continue;
+        g.csplit = cs; g.n_split = cs; g.split_len = len;
+        break;
+      }
+    }
+    if (!g.csplit && want > 1) {
       g.split_len = (g.k_items + want - 1) / want;
       g.n_split = (g.k_items + g.split_len - 1) / g.split_len;
       if (g.n_split > 1) g.partial_bytes = static_cast<size_t>(g.n_split) * g.tiles_per_split * kTileM * g.bn * sizeof(float);
@@ -697,7 +712,9 @@ int build_plan(lspg_ctx* h, Plan* P, int B, int H, int W, int mode, void* worksp
     // Split-K is two-pass: raw fp32 partials, then splitk_reduce_kernel.  (Measured on B200 in round 1: letting the
     // last-arriving CTA sum the partials in-kernel was slower - one CTA's epilogue threads reduce a tile far more slowly
     // than a grid of them - so that variant was removed.)
-    pl.split = g.n_split > 1;
+    pl.split = g.n_split > 1 && g.csplit == 0;
+    pl.csplit = g.csplit;
+    p.cluster_split = g.csplit ? 1 : 0;
     p.n_taps = L.n_taps; p.n_src = L.n_src;
     p.chunks[0] = L.cin[0] / 64; p.chunks[1] = L.n_src == 2 ? L.cin[1] / 64 : 0;
     p.relu = L.relu; p.has_res = L.res >= 0 ? 1 : 0;
@@ -841,27 +858,27 @@ int ensure_smem(K kernel, int bytes, int device, unsigned long long* done_mask) 
 
 const void* g_last_func = nullptr;     // host stub of the most recent conv launch (identifies graph nodes after capture)
 
-template <int BN, int NL, bool TAIL>
-int launch_conv(const ConvParams& p, int grid, int device, cudaStream_t st) {
-  using Cfg = ConvCfg<BN, NL, TAIL>;
+template <int BN, int NL, bool TAIL, bool CSP = false>
+int launch_conv(const ConvParams& p, int grid, int device, cudaStream_t st, int cluster = 1) {
+  using Cfg = ConvCfg<BN, NL, TAIL, CSP>;
   static unsigned long long done = 0;
-  int rc = ensure_smem(conv_umma_kernel<BN, NL, TAIL>, Cfg::kSmemBytes, device, &done);
+  int rc = ensure_smem(conv_umma_kernel<BN, NL, TAIL, CSP>, Cfg::kSmemBytes, device, &done);
   if (rc) return rc;
-  g_last_func = reinterpret_cast<const void*>(conv_umma_kernel<BN, NL, TAIL>);
-  CUDA_TRY(launch_pdl(conv_umma_kernel<BN, NL, TAIL>, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, st, p));
+  g_last_func = reinterpret_cast<const void*>(conv_umma_kernel<BN, NL, TAIL, CSP>);
+  CUDA_TRY(launch_pdl_cluster(conv_umma_kernel<BN, NL, TAIL, CSP>, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, st, cluster, p));
   return LSPG_OK;
 }
 
 // Epilogue warps: 4 for the tail (one fp32 / uint8 scatter per pixel), 8 for every other patch / pair kernel.
-template <int BN, int NL, bool TAIL, int CL>
-int launch_patch(const ConvParams& p, int grid, int device, cudaStream_t st) {
-  using Cfg = PatchCfg<BN, NL, TAIL>;
+template <int BN, int NL, bool TAIL, int CL, bool CSP = false>
+int launch_patch(const ConvParams& p, int grid, int device, cudaStream_t st, int cluster = CL) {
+  using Cfg = PatchCfg<BN, NL, TAIL, CSP>;
   constexpr int EW = TAIL ? 4 : 8;
   static unsigned long long done = 0;
-  int rc = ensure_smem(conv_patch_kernel<BN, NL, TAIL, CL, EW>, Cfg::kSmemBytes, device, &done);
+  int rc = ensure_smem(conv_patch_kernel<BN, NL, TAIL, CL, EW, CSP>, Cfg::kSmemBytes, device, &done);
   if (rc) return rc;
-  g_last_func = reinterpret_cast<const void*>(conv_patch_kernel<BN, NL, TAIL, CL, EW>);
-  CUDA_TRY(launch_pdl_cluster(conv_patch_kernel<BN, NL, TAIL, CL, EW>, dim3(grid), dim3(64 + EW * 32), Cfg::kSmemBytes, st, CL, p));
+  g_last_func = reinterpret_cast<const void*>(conv_patch_kernel<BN, NL, TAIL, CL, EW, CSP>);
+  CUDA_TRY(launch_pdl_cluster(conv_patch_kernel<BN, NL, TAIL, CL, EW, CSP>, dim3(grid), dim3(64 + EW * 32), Cfg::kSmemBytes, st, cluster, p));
   return LSPG_OK;
 }
 
@@ -887,6 +904,12 @@ int launch_layer(const PlanLayer& pl, int kind, int NL, int device, cudaStream_t
     if (pl.bn == 256) return NL == 1 ? launch_pair<256, 1>(pl.prm, pl.grid, device, st) : launch_pair<256, 2>(pl.prm, pl.grid, device, st);
     if (pl.bn == 64) return NL == 1 ? launch_pair<64, 1>(pl.prm, pl.grid, device, st) : launch_pair<64, 2>(pl.prm, pl.grid, device, st);
     return NL == 1 ? launch_pair<128, 1>(pl.prm, pl.grid, device, st) : launch_pair<128, 2>(pl.prm, pl.grid, device, st);
+  }
+  if (pl.csplit) {          // split-K inside a cluster of pl.csplit CTAs (one tile per CTA, grid = tiles x csplit)
+    const int cs = pl.csplit;
+    if (pl.patch) return NL == 1 ? launch_patch<64, 1, false, 1, true>(pl.prm, pl.grid, device, st, cs) : launch_patch<64, 2, false, 1, true>(pl.prm, pl.grid, device, st, cs);
+    if (pl.bn == 128) return NL == 1 ? launch_conv<128, 1, false, true>(pl.prm, pl.grid, device, st, cs) : launch_conv<128, 2, false, true>(pl.prm, pl.grid, device, st, cs);
+    return NL == 1 ? launch_conv<64, 1, false, true>(pl.prm, pl.grid, device, st, cs) : launch_conv<64, 2, false, true>(pl.prm, pl.grid, device, st, cs);
   }
   if (pl.patch) {
     const int c = pl.cluster;
@@ -1331,6 +1354,7 @@ int lspg_debug_layer_geo(lspg_handle h, int layer, int batch, int height, int wi
   if (g.pair) ctas -= ctas % 2;
   o->ctas = ctas;
   o->partial_bytes = static_cast<int64_t>(g.partial_bytes);
+  o->cluster_split = g.csplit;
   return LSPG_OK;
 }
 

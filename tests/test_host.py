@@ -235,11 +235,21 @@ def test_planner_invariants(variant, batch):
             assert g.kernel != 2
             assert tiles * g.n_split <= sms                                  # split-K never spills into a second wave
             assert (g.n_split - 1) * g.split_len < g.k_items <= g.n_split * g.split_len   # every split has work
-            assert g.partial_bytes == g.n_split * tiles * 128 * g.bn * 4
+            if g.cluster_split:
+                # the splits of a tile are one thread-block cluster (DSMEM reduction): portable cluster size, one CTA per
+                # (tile, split), nothing in the global scratch, no finisher launch
+                assert g.cluster_split == g.n_split and g.n_split in (2, 4, 8)
+                assert g.ctas == tiles * g.n_split and g.partial_bytes == 0
+                assert g.bn in (64, 128) and info.kind != 4
+            else:
+                assert g.partial_bytes == g.n_split * tiles * 128 * g.bn * 4
         else:
-            assert g.partial_bytes == 0
+            assert g.partial_bytes == 0 and g.cluster_split == 0
         assert 1 <= g.ctas <= sms
     assert ws > max(g.partial_bytes for _, g in table)
+    if batch == 1:
+        # batch 1 (demo.py's call pattern): every layer from 64x64 down splits K, all of them inside clusters
+        assert sum(1 for _, g in table if g.cluster_split) >= 40 and not any(g.n_split > 1 and not g.cluster_split for _, g in table)
 
 
 def test_planner_picks_the_n_tile_with_fewer_waves():
