@@ -684,7 +684,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16" if args.mode == "fast" else "bf16 hi+lo split operands (3 tcgen05 MMAs per K step), fp32 accumulate",
+            "dtype": "bf16" if args.mode == "fast" else "fp16 hi+lo split operands (3 tcgen05 MMAs per K step), fp32 accumulate",
             "data": "synthetic (seeded weights with the reference's init distribution - no checkpoint ships; seeded inputs)",
             "config": config_dict(args, world),
             "max_abs_err_vs_oracle": parity_err, "max_abs_err_note": parity_note,

@@ -36,8 +36,9 @@ extern "C" {
 #define LSPG_VARIANT_LARGE 1
 
 /* Precision modes.  FAST: bf16 operands, fp32 accumulate (1 MMA / K step).
- * PARITY: bf16 hi+lo split operands, hi*hi + hi*lo + lo*hi, fp32 accumulate (3 MMAs / K step);
- * this is the mode that meets the 1e-3 max-abs contract against the fp32 reference. */
+ * PARITY: fp16 hi+lo split operands (22 mantissa bits), hi*hi + hi*lo + lo*hi, fp32 accumulate (3 MMAs / K step);
+ * this is the mode that meets the 1e-3 max-abs contract against the fp32 reference.  Activations are stored as fp16
+ * limbs: values beyond +-65504 saturate (the network's activations are O(1..100)). */
 #define LSPG_MODE_FAST 0
 #define LSPG_MODE_PARITY 1
 
@@ -146,14 +147,17 @@ int lspg_debug_fast_div(uint32_t n, uint32_t d, uint32_t* q);
 
 int lspg_num_layers(lspg_handle h, int* out);
 int lspg_layer_info_get(lspg_handle h, int layer, lspg_layer_info* out);
-/* Packed weights as the kernels see them: bf16 bit patterns, limb 0 = hi, limb 1 = lo (w - hi);
- * `count` must be n_phases*cout_pad*k_total.  scale/shift: cout_pad floats each. */
+/* Packed weights as the kernels see them, 16-bit patterns: limb 0 / 1 = PARITY operands, fp16 hi and lo (v - hi) limbs of
+ * v = w * LSPG_PARITY_WEIGHT_SCALE (the epilogue scale carries the inverse); limb 2 = FAST operand, bf16(w).
+ * `count` must be n_phases*cout_pad*k_total.  scale/shift: cout_pad floats each (the unscaled BatchNorm fold). */
+#define LSPG_PARITY_WEIGHT_SCALE 256.0f
 int lspg_layer_packed(lspg_handle h, int layer, int limb, uint16_t* dst, int64_t count);
 int lspg_layer_affine(lspg_handle h, int layer, float* scale, float* shift, int64_t count);
 /* Activation tensor table for (batch,height,width): per-image channels/height/width of tensor `id`. */
 int lspg_num_tensors(lspg_handle h, int* out);
 int lspg_tensor_shape(lspg_handle h, int id, int height, int width, int* c, int* th, int* tw);
-/* Copy activation tensor `id` (bf16 NHWC, limb 0 or 1) of the most recent forward to host memory. */
+/* Copy activation tensor `id` (16-bit NHWC: bf16 after a FAST forward, fp16 limb 0 or 1 after a PARITY forward) of the most
+ * recent forward to host memory. */
 int lspg_debug_read_tensor(lspg_handle h, int id, int limb, uint16_t* dst, int64_t count);
 /* Debug: with LSPG_TRACE_LAYER=<i> in the environment the conv kernel of layer i stamps clock64() at its pipeline
  * milestones (conv_umma.cuh: kTraceSlots values per CTA, 256 CTAs); this copies them out. */

@@ -1,13 +1,14 @@
 // Memory-bound helper kernels around the conv stack.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cstdint>
 
 namespace lspg {
 
 // Input packer: fuses Feature2FaceModel.inference's torch.cat([feature_map, cand_image], 1)
-// (reference models/feature2face_model.py:231), the NCHW->NHWC transpose, the fp32->bf16 conversion (hi and,
-// in parity mode, lo limb) and a 2x2 space-to-depth, so that the stride-2 head conv (13->64,
+// (reference models/feature2face_model.py:231), the NCHW->NHWC transpose, the fp32->16-bit conversion (bf16 in FAST mode,
+// fp16 hi + lo limbs in PARITY mode) and a 2x2 space-to-depth, so that the stride-2 head conv (13->64,
 // models/networks.py:594-595 with input_nc=13) becomes a 4-tap stride-1 conv over a 64-channel tensor:
 //   S[n, oy, ox, (py*2+px)*16 + c] = x[n, c, 2*oy+py, 2*ox+px]   (c < in_nc; channels in_nc..15 are zero)
 // One thread per output pixel, one warp per 32 consecutive pixels of an output row: the float2 reads are coalesced along W
@@ -50,12 +51,14 @@ __global__ void __launch_bounds__(kPackWarps * 32) pack_input_s2d_kernel(const f
 #pragma unroll
           for (int px = 0; px < 2; ++px) {
             const int ch = (py * 2 + px) * 16 + c;
-            const __nv_bfloat16 h = __float2bfloat16_rn(vv[px]);
-            const uint32_t hb = static_cast<uint32_t>(__bfloat16_as_ushort(h));
-            hi[ch >> 1] |= hb << ((ch & 1) * 16);
-            if (NL == 2) {
-              const __nv_bfloat16 l = __float2bfloat16_rn(vv[px] - __bfloat162float(h));
-              lo[ch >> 1] |= static_cast<uint32_t>(__bfloat16_as_ushort(l)) << ((ch & 1) * 16);
+            if (NL == 2) {                      // PARITY: fp16 hi + lo limbs (inputs are in [-1, 1]: no range concern)
+              const __half h = __float2half_rn(vv[px]);
+              hi[ch >> 1] |= static_cast<uint32_t>(__half_as_ushort(h)) << ((ch & 1) * 16);
+              const __half l = __float2half_rn(vv[px] - __half2float(h));
+              lo[ch >> 1] |= static_cast<uint32_t>(__half_as_ushort(l)) << ((ch & 1) * 16);
+            } else {                            // FAST: bf16
+              const __nv_bfloat16 h = __float2bfloat16_rn(vv[px]);
+              hi[ch >> 1] |= static_cast<uint32_t>(__bfloat16_as_ushort(h)) << ((ch & 1) * 16);
             }
           }
         }

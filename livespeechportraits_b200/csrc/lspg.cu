@@ -62,6 +62,13 @@ float bf16_to_f32(uint16_t h) {
   memcpy(&f, &u, 4);
   return f;
 }
+uint16_t f32_to_f16(float f) { return __half_as_ushort(__float2half_rn(f)); }     // round to nearest even, subnormals kept
+float f16_to_f32(uint16_t h) { return __half2float(__ushort_as_half(h)); }
+
+// PARITY packs weights as fp16 hi + lo limbs of (w * 2^kParityWeightShift): with the reference's N(0, 0.02) weights the lo
+// limb of an unscaled weight sits in fp16's subnormal range; pre-scaling by a power of two (exact) moves it into the normal
+// range, and the epilogue's folded BatchNorm scale carries the inverse factor (exact as well).
+constexpr int kParityWeightShift = 8;
 
 struct TensorInfo {
   int channels;
@@ -83,12 +90,15 @@ struct Layer {
   // parameters (host, fp32, as loaded) and their packed forms
   std::vector<float> w;                      // OIHW
   std::vector<float> bn_w, bn_b, bn_m, bn_v;
-  std::vector<uint16_t> packed[2];           // [limb][phase][cout_pad][k_total]
+  std::vector<uint16_t> packed[3];           // [phase][cout_pad][k_total] each: 0/1 = PARITY fp16 hi/lo limbs of w * 2^8, 2 = FAST bf16
   std::vector<float> scale, shift;           // [cout_pad]
+  std::vector<float> scale_par;              // scale * 2^-8 (PARITY weights are pre-scaled)
   bool dirty = true;
   bool has_w = false;                        // the conv weight has been supplied at least once (forward refuses otherwise)
   // device copies
-  uint16_t* d_w = nullptr;                   // [limb][phase][cout_pad][k_total]
+  uint16_t* d_w = nullptr;                   // PARITY: [limb][phase][cout_pad][k_total] fp16
+  uint16_t* d_w_fast = nullptr;              // FAST:   [phase][cout_pad][k_total] bf16
+  float* d_scale_par = nullptr;
   float* d_scale = nullptr;
   float* d_shift = nullptr;
 };
@@ -393,11 +403,14 @@ void pack_layer(lspg_ctx* h, Layer& L) {
             }
         }
   }
-  for (int l = 0; l < 2; ++l) L.packed[l].assign(P.size(), 0);
+  for (int l = 0; l < 3; ++l) L.packed[l].assign(P.size(), 0);
+  const float up = static_cast<float>(1 << kParityWeightShift);
   for (size_t i = 0; i < P.size(); ++i) {
-    const uint16_t hi = f32_to_bf16(P[i]);
+    const float ws = P[i] * up;                           // exact (power of two)
+    const uint16_t hi = f32_to_f16(ws);
     L.packed[0][i] = hi;
-    L.packed[1][i] = f32_to_bf16(P[i] - bf16_to_f32(hi));
+    L.packed[1][i] = f32_to_f16(ws - f16_to_f32(hi));
+    L.packed[2][i] = f32_to_bf16(P[i]);
   }
   L.scale.assign(L.cout_pad, 1.0f);
   L.shift.assign(L.cout_pad, 0.0f);
@@ -408,6 +421,8 @@ void pack_layer(lspg_ctx* h, Layer& L) {
       L.shift[o] = L.bn_b[o] - L.bn_m[o] * L.scale[o];
     }
   }
+  L.scale_par.resize(L.cout_pad);
+  for (int o = 0; o < L.cout_pad; ++o) L.scale_par[o] = L.scale[o] / up;      // exact
 }
 
 int upload_layer(lspg_ctx* h, Layer& L) {
@@ -415,12 +430,16 @@ int upload_layer(lspg_ctx* h, Layer& L) {
   const size_t n = L.packed[0].size();
   if (!L.d_w) {
     CUDA_TRY(cudaMalloc(&L.d_w, 2 * n * sizeof(uint16_t)));
+    CUDA_TRY(cudaMalloc(&L.d_w_fast, n * sizeof(uint16_t)));
     CUDA_TRY(cudaMalloc(&L.d_scale, L.cout_pad * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&L.d_scale_par, L.cout_pad * sizeof(float)));
     CUDA_TRY(cudaMalloc(&L.d_shift, L.cout_pad * sizeof(float)));
   }
   CUDA_TRY(cudaMemcpy(L.d_w, L.packed[0].data(), n * 2, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(L.d_w + n, L.packed[1].data(), n * 2, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(L.d_w_fast, L.packed[2].data(), n * 2, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(L.d_scale, L.scale.data(), L.cout_pad * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(L.d_scale_par, L.scale_par.data(), L.cout_pad * 4, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(L.d_shift, L.shift.data(), L.cout_pad * 4, cudaMemcpyHostToDevice));
   return LSPG_OK;
 }
@@ -587,7 +606,7 @@ int make_act_map(lspg_ctx* h, CUtensorMap* m, void* base, size_t limb_stride, in
   strides[3] = NL > 1 ? limb_stride : strides[2] * B;
   cuuint32_t box[5] = {64u, static_cast<cuuint32_t>(tw), static_cast<cuuint32_t>(th), static_cast<cuuint32_t>(nb), 1u};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = h->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, p, dims, strides, box, estr,
+  CUresult r = h->encode(m, NL > 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, p, dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
@@ -596,14 +615,15 @@ int make_act_map(lspg_ctx* h, CUtensorMap* m, void* base, size_t limb_stride, in
   return LSPG_OK;
 }
 
-int make_weight_map(lspg_ctx* h, CUtensorMap* m, const Layer& L, int bn) {
+int make_weight_map(lspg_ctx* h, CUtensorMap* m, const Layer& L, int bn, int NL) {
   cuuint64_t dims[3] = {static_cast<cuuint64_t>(L.k_total), static_cast<cuuint64_t>(L.cout_pad),
-                        static_cast<cuuint64_t>(2 * L.n_phases)};
+                        static_cast<cuuint64_t>(NL * L.n_phases)};
   cuuint64_t strides[2] = {static_cast<cuuint64_t>(L.k_total) * 2,
                            static_cast<cuuint64_t>(L.k_total) * L.cout_pad * 2};
   cuuint32_t box[3] = {64u, static_cast<cuuint32_t>(bn), 1u};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = h->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, L.d_w, dims, strides, box, estr,
+  CUresult r = h->encode(m, NL > 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, NL > 1 ? L.d_w : L.d_w_fast, dims,
+                         strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(LSPG_ECUDA, "cuTensorMapEncodeTiled(weights K=%d) failed: %d", L.k_total, static_cast<int>(r));
@@ -612,15 +632,16 @@ int make_weight_map(lspg_ctx* h, CUtensorMap* m, const Layer& L, int bn) {
 
 // Patch-mode weight view {kc, Cout, tap, limb*phase}: K of the packed weights is tap-major, so the tap index is a
 // dimension of its own and one TMA box {64, BN, taps_per_stage, 1} fetches the tiles of several taps at once.
-int make_weight_map_taps(lspg_ctx* h, CUtensorMap* m, const Layer& L, int bn, int tps) {   // bn = box rows, tps = box taps
+int make_weight_map_taps(lspg_ctx* h, CUtensorMap* m, const Layer& L, int bn, int tps, int NL) {   // bn = box rows, tps = box taps
   const int kt = L.k_total / L.n_taps;       // K elements per tap
   cuuint64_t dims[4] = {static_cast<cuuint64_t>(kt), static_cast<cuuint64_t>(L.cout_pad), static_cast<cuuint64_t>(L.n_taps),
-                        static_cast<cuuint64_t>(2 * L.n_phases)};
+                        static_cast<cuuint64_t>(NL * L.n_phases)};
   cuuint64_t strides[3] = {static_cast<cuuint64_t>(L.k_total) * 2, static_cast<cuuint64_t>(kt) * 2,
                            static_cast<cuuint64_t>(L.k_total) * L.cout_pad * 2};
   cuuint32_t box[4] = {64u, static_cast<cuuint32_t>(bn), static_cast<cuuint32_t>(tps), 1u};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = h->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, L.d_w, dims, strides, box, estr,
+  CUresult r = h->encode(m, NL > 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, NL > 1 ? L.d_w : L.d_w_fast, dims,
+                         strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(LSPG_ECUDA, "cuTensorMapEncodeTiled(weights by tap, K=%d) failed: %d", L.k_total, static_cast<int>(r));
@@ -633,13 +654,15 @@ int patch_tps(int bn, int NL, bool tail) {   // must mirror PatchCfg::kTPS
   return NL == 1 ? 3 : 2;
 }
 
-uint32_t make_idesc(int bn, int m = kTileM) {
-  // cute::UMMA::InstrDescriptor bit layout: c_format[4,6)=1 (F32), a_format[7,10)=1 (BF16), b_format[10,13)=1,
+uint32_t make_idesc(int bn, int m, bool f16) {
+  // cute::UMMA::InstrDescriptor bit layout: c_format[4,6)=1 (F32), a_format[7,10) and b_format[10,13): 0 = F16, 1 = BF16,
   // a/b major [15],[16] = 0 (K-major), n_dim[17,23) = N>>3, m_dim[24,29) = M>>4
   uint32_t d = 0;
   d |= 1u << 4;
-  d |= 1u << 7;
-  d |= 1u << 10;
+  if (!f16) {
+    d |= 1u << 7;
+    d |= 1u << 10;
+  }
   d |= static_cast<uint32_t>(bn >> 3) << 17;
   d |= static_cast<uint32_t>(m >> 4) << 24;
   return d;
@@ -719,9 +742,10 @@ int build_plan(lspg_ctx* h, Plan* P, int B, int H, int W, int mode, void* worksp
     p.chunks[0] = L.cin[0] / 64; p.chunks[1] = L.n_src == 2 ? L.cin[1] / 64 : 0;
     p.relu = L.relu; p.has_res = L.res >= 0 ? 1 : 0;
     p.batch = B; p.hs = Hs; p.ws = Ws;
-    p.idesc = g.pair ? make_idesc(pl.bn, 256) : make_idesc(pl.bn);
-    p.idesc2 = g.pair ? make_idesc(2 * pl.bn > 256 ? 256 : 2 * pl.bn, 256) : make_idesc(2 * pl.bn > 256 ? 256 : 2 * pl.bn);
-    p.scale = L.d_scale; p.shift = L.d_shift; p.out_f32 = nullptr;
+    const bool f16 = NL > 1;                  // PARITY operands are fp16 limbs, FAST operands bf16
+    p.idesc = make_idesc(pl.bn, g.pair ? 256 : kTileM, f16);
+    p.idesc2 = make_idesc(2 * pl.bn > 256 ? 256 : 2 * pl.bn, g.pair ? 256 : kTileM, f16);
+    p.scale = f16 ? L.d_scale_par : L.d_scale; p.shift = L.d_shift; p.out_f32 = nullptr;
     memcpy(p.tap_map, L.tap_map, sizeof(p.tap_map));
     memcpy(p.tap_dx, L.tap_dx, sizeof(p.tap_dx));
     memcpy(p.tap_dy, L.tap_dy, sizeof(p.tap_dy));
@@ -746,11 +770,11 @@ int build_plan(lspg_ctx* h, Plan* P, int B, int H, int W, int mode, void* worksp
       static const bool no_cluster = getenv("LSPG_NO_CLUSTER") != nullptr;
       pl.pair = g.pair;
       pl.cluster = (g.pair || (!no_cluster && g.n_split == 1 && g.m_tiles % 2 == 0 && g.tiles_per_split >= h->num_sms)) ? 2 : 1;
-      if (pl.cluster == 1 && NL == 1 && !pl.pair) rc = make_weight_map_taps(h, &p.w, L, pl.bn, patch_tps(pl.bn, NL, L.kind == K_TAIL));
-      else rc = make_weight_map_taps(h, &p.w, L, pl.bn / pl.cluster, 1);      // per-tap boxes (row slice per CTA when multicasting)
+      if (pl.cluster == 1 && NL == 1 && !pl.pair) rc = make_weight_map_taps(h, &p.w, L, pl.bn, patch_tps(pl.bn, NL, L.kind == K_TAIL), NL);
+      else rc = make_weight_map_taps(h, &p.w, L, pl.bn / pl.cluster, 1, NL);      // per-tap boxes (row slice per CTA when multicasting)
       if (rc) return rc;
     } else {
-      if ((rc = make_weight_map(h, &p.w, L, pl.bn))) return rc;
+      if ((rc = make_weight_map(h, &p.w, L, pl.bn, NL))) return rc;
     }
     // ---- output / residual views
     if (L.kind != K_TAIL) {
@@ -790,10 +814,14 @@ int build_plan(lspg_ctx* h, Plan* P, int B, int H, int W, int mode, void* worksp
         p.trace_skip = ts ? atoi(ts) : 0;
       }
     }
+    {
+      const char* fl = getenv("LSPG_DEBUG_FAULT_LAYER");      // test hook: see ConvParams::debug_fault
+      if (fl && atoi(fl) == static_cast<int>(P->layers.size()) && !g.patch) p.debug_fault = 1;
+    }
     if (pl.split) {
       ReduceParams& r = pl.red;
       memset(&r, 0, sizeof(r));
-      r.partial = p.partial; r.scale = L.d_scale; r.shift = L.d_shift;
+      r.partial = p.partial; r.scale = p.scale; r.shift = L.d_shift;
       r.out = reinterpret_cast<__nv_bfloat16*>(ws + P->tensor_off[L.out]);
       r.out_limb_stride = static_cast<long long>(P->tensor_limb_stride[L.out] / 2);
       if (L.res >= 0) {
@@ -1103,6 +1131,8 @@ int lspg_destroy(lspg_handle h) {
     cudaSetDevice(h->device);
     for (auto& L : h->layers) {
       if (L.d_w) cudaFree(L.d_w);
+      if (L.d_w_fast) cudaFree(L.d_w_fast);
+      if (L.d_scale_par) cudaFree(L.d_scale_par);
       if (L.d_scale) cudaFree(L.d_scale);
       if (L.d_shift) cudaFree(L.d_shift);
     }
@@ -1289,7 +1319,7 @@ int lspg_layer_info_get(lspg_handle h, int layer, lspg_layer_info* o) {
 
 int lspg_layer_packed(lspg_handle h, int layer, int limb, uint16_t* dst, int64_t count) {
   if (!h || !dst) return fail(LSPG_EINVAL, "null argument");
-  if (layer < 0 || layer >= static_cast<int>(h->layers.size()) || limb < 0 || limb > 1) return fail(LSPG_EINVAL, "bad layer/limb");
+  if (layer < 0 || layer >= static_cast<int>(h->layers.size()) || limb < 0 || limb > 2) return fail(LSPG_EINVAL, "bad layer/limb");
   const Layer& L = h->layers[layer];
   if (L.packed[limb].empty()) return fail(LSPG_ESTATE, "weights not loaded");
   if (static_cast<size_t>(count) != L.packed[limb].size()) return fail(LSPG_EINVAL, "count %lld != %zu", static_cast<long long>(count), L.packed[limb].size());

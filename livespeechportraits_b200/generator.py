@@ -379,10 +379,13 @@ class Feature2Face_G(nn.Module):
                              out=info.out, res=info.res))
         return rows
 
-    def debug_read_tensor(self, tensor_id: int, batch: int, height: int, width: int, limb: int = 0) -> torch.Tensor:
+    def debug_read_tensor(self, tensor_id: int, batch: int, height: int, width: int, limb: int = 0,
+                          precision: Optional[str] = None) -> torch.Tensor:
+        """Activation tensor of the most recent forward: fp16 limbs after a PARITY forward, bf16 after a FAST one."""
         c, th, tw = C.c_int(), C.c_int(), C.c_int()
         _lib.check(self._lib.lspg_tensor_shape(self._handle, tensor_id, height, width, C.byref(c), C.byref(th), C.byref(tw)))
-        buf = torch.empty((batch, th.value, tw.value, c.value), dtype=torch.bfloat16)
+        dt = torch.float16 if (precision or self.precision) == "parity" else torch.bfloat16
+        buf = torch.empty((batch, th.value, tw.value, c.value), dtype=dt)
         _lib.check(self._lib.lspg_debug_read_tensor(self._handle, tensor_id, limb, buf.data_ptr(), buf.numel()))
         return buf
 

@@ -14,8 +14,8 @@ schemes (tensor cost in bf16-MMA equivalents per K step):
   f16_a2      2.0   fp16 hi+lo activations x fp16 weights
   f16_f8corr  2.0   fp16 x fp16 + one K-doubled fp8 (e4m3) MMA for a_lo*w_hi + a_hi*w_lo, power-of-two scales
   f16_f8e5m2  2.0   same with e5m2 activations (range-safe, 3-bit significand)
-  bf16x3      3.0   bf16 hi*hi + hi*lo + lo*hi                      (PARITY mode)
-  f16x3       3.0   fp16 hi*hi + hi*lo + lo*hi                      (22-bit operands: the "free margin" variant)
+  bf16x3      3.0   bf16 hi*hi + hi*lo + lo*hi                      (PARITY mode of round 1)
+  f16x3       3.0   fp16 hi*hi + hi*lo + lo*hi                      (22-bit operands, same tensor cost: PARITY mode since round 2)
 
     python oracle/precision_study.py --mix                # round-2 question: can SOME layers run a 2-pass scheme?
 runs large/B at 512x512 (the case with the least margin) with the 2-pass scheme f16_f8corr on one class of layers at a

@@ -53,14 +53,23 @@ class HostPlan:
             self.lib.lspg_destroy(self.h)
             self.h = C.c_void_p()
 
+    PARITY_WEIGHT_SCALE = 256.0          # include/lspg.h: LSPG_PARITY_WEIGHT_SCALE
+
     def packed(self, i: int, limbs: int) -> torch.Tensor:
+        """Weights as the kernels multiply them: ``limbs == 2`` = PARITY (fp16 hi + lo limbs of w * 256, scaled back here),
+        ``limbs == 1`` = FAST (bf16)."""
         L = self.layers[i]
         count = L.n_phases * L.cout_pad * L.k_total
-        out = torch.zeros(count)
-        for limb in range(limbs):
-            buf = np.zeros(count, np.uint16)
-            _lib.check(self.lib.lspg_layer_packed(self.h, i, limb, buf.ctypes.data, count))
-            out += bf16_bits_to_f32(buf)
+        buf = np.zeros(count, np.uint16)
+        if limbs == 1:
+            _lib.check(self.lib.lspg_layer_packed(self.h, i, 2, buf.ctypes.data, count))
+            out = bf16_bits_to_f32(buf)
+        else:
+            out = torch.zeros(count)
+            for limb in range(2):
+                _lib.check(self.lib.lspg_layer_packed(self.h, i, limb, buf.ctypes.data, count))
+                out += torch.from_numpy(buf.view(np.float16).astype(np.float32))
+            out = out / self.PARITY_WEIGHT_SCALE
         return out.view(L.n_phases, L.cout_pad, L.k_total)
 
     def affine(self, i: int):
@@ -94,7 +103,7 @@ def pack_input_s2d(x: torch.Tensor) -> torch.Tensor:
 
 def run_plan(plan: HostPlan, x: torch.Tensor, limbs: int = 2, round_act=None,
              taps_out: Optional[Dict[int, torch.Tensor]] = None) -> torch.Tensor:
-    """Execute the plan on [B,13,H,W] fp32 input.  ``limbs``: 1 = bf16 weights, 2 = hi+lo weights.
+    """Execute the plan on [B,13,H,W] fp32 input.  ``limbs``: 1 = FAST (bf16 weights), 2 = PARITY (fp16 hi+lo weights).
     ``round_act``: optional function applied to every stored activation (e.g. bf16 rounding)."""
     q = round_act or (lambda t: t)
     tensors: Dict[int, torch.Tensor] = {0: q(pack_input_s2d(x))}
