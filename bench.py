@@ -504,7 +504,7 @@ def main():
         def e2e_once(n_chunks):
             nl = n_chunks * B
             fm_dev[:nl].copy_(fm_host[:nl], non_blocking=True)
-            return sr8.render(nl * world, fm_dev[:nl], host_out=(host_out[: nl * world] if rank == 0 else None))
+            return sr8.render(nl * world, fm_dev[:nl], host_out=(host_out[: nl * world] if rank == 0 else None), to_host=True)
         e2e_once(min(3, K))
         barrier()
         t0 = time.perf_counter()
@@ -521,7 +521,7 @@ def main():
         e2e = {"value": n_all / dt, "unit": "frames/s", "h2d_bytes_per_step": B * H * W * 4,
                "d2h_bytes_per_step": world * B * H * W * 3, "frames": n_all, "seconds": dt, "gather_mode": sr8.gather_mode,
                "host_copy_matches_device_clip": e2e_ok,
-               "api": "parallel.ShardedRenderer(uint8=True).render(host_out=...): per-rank pinned feature maps -> H2D -> render -> "
+               "api": "parallel.ShardedRenderer(uint8=True).render(host_out=..., to_host=True): per-rank pinned feature maps -> H2D -> render -> "
                       "frames to every rank -> rank 0 copies the whole gathered clip (uint8 HWC images, util.tensor2im fused) to "
                       "pinned host memory; d2h bytes are rank 0's per step"}
         del host_out, fm_dev

@@ -128,15 +128,21 @@ class ShardedRenderer:
 
     # ------------------------------------------------------------------ render
     def render(self, n_total: int, local_feature_maps: torch.Tensor, gather: bool = True,
-               host_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+               host_out: Optional[torch.Tensor] = None, to_host: bool = False) -> torch.Tensor:
         """``local_feature_maps``: this rank's block ``partition(n_total, world, rank)`` of the clip, on this rank's device.
 
         Returns ``[n_total, ...]`` (every rank holds all frames, frame order = clip order) when ``gather``, else this
-        rank's ``[n_local, ...]``.  ``host_out`` (pinned ``[n_total, ...]``, optional, honoured on rank 0 only): the
-        gathered frames are also copied to host memory chunk by chunk while later chunks render; the call returns after
-        the last copy has landed.  In "ce" mode the returned tensor is the renderer's symmetric clip buffer: it is
-        overwritten by the next ``render`` of the same shape.
+        rank's ``[n_local, ...]``.  ``to_host=True`` (a COLLECTIVE choice: pass the same value on every rank) delivers the
+        gathered frames to rank 0's ``host_out`` (pinned ``[n_total, ...]``, needed on rank 0 only) chunk by chunk while
+        later chunks render; the call returns after the last copy has landed.  In "ce" mode the returned tensor is the
+        renderer's symmetric clip buffer: it is overwritten by the next ``render`` of the same shape.
         """
+        if host_out is not None and not to_host and self.world > 1:
+            raise ValueError("host_out needs to_host=True on EVERY rank (the per-chunk completion barrier is collective)")
+        if to_host and self.rank == 0 and host_out is None and gather:
+            raise ValueError("to_host=True: rank 0 must supply host_out")
+        if self.rank != 0:
+            host_out = None
         start, stop = partition(n_total, self.world, self.rank)
         n_local = stop - start
         if local_feature_maps.shape[0] != n_local:
@@ -163,11 +169,12 @@ class ShardedRenderer:
             return out
         mode = self._decide_mode(n_total, h, w, dev)
         if mode == "ce":
-            return self._render_ce(n_total, local_feature_maps, host_out)
+            return self._render_ce(n_total, local_feature_maps, host_out, to_host)
         return self._render_nccl(n_total, local_feature_maps, host_out)
 
     # ------------------------------------------------------------------ copy-engine push over symmetric memory
-    def _render_ce(self, n_total: int, local_feature_maps: torch.Tensor, host_out: Optional[torch.Tensor]) -> torch.Tensor:
+    def _render_ce(self, n_total: int, local_feature_maps: torch.Tensor, host_out: Optional[torch.Tensor],
+                   to_host: bool) -> torch.Tensor:
         dev = local_feature_maps.device
         h, w = local_feature_maps.shape[-2:]
         clip, hdl, peers = self._symmetric_clip(n_total, h, w, dev)
@@ -178,7 +185,7 @@ class ShardedRenderer:
         cur = torch.cuda.current_stream(dev)
         streams = self._copy_streams(dev)
         others = [(self.rank + k) % self.world for k in range(1, self.world)]       # staggered: ranks start on different peers
-        per_chunk_sync = host_out is not None
+        per_chunk_sync = bool(to_host)          # identical on every rank: the per-chunk barrier below is collective
         d2h = torch.cuda.Stream(device=dev) if (per_chunk_sync and self.rank == 0) else None
         # nobody may still be reading the previous clip out of this buffer / pushing into it
         hdl.barrier(channel=0)

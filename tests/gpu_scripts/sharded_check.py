@@ -55,7 +55,7 @@ def main():
                 sr = ShardedRenderer(fn, chunk=chunk, uint8=uint8, gather=mode)
                 host = torch.empty(shape, dtype=exp.dtype).pin_memory() if rank == 0 else None
                 t0 = time.perf_counter()
-                got = sr.render(n_total, fm_all[s:e].to(dev), host_out=host)
+                got = sr.render(n_total, fm_all[s:e].to(dev), host_out=host, to_host=True)
                 torch.cuda.synchronize()
                 dt = time.perf_counter() - t0
                 same = bool(torch.equal(got, exp))

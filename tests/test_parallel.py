@@ -53,7 +53,7 @@ def _worker(rank, world, port, n_total, chunk, gather, uint8, to_host, q):
         exp = torch.empty((n_total, 8, 8, 3), dtype=torch.uint8) if uint8 else torch.empty(n_total, 3, 8, 8)
         fn(clip, exp)
         host = torch.zeros_like(exp) if to_host else None
-        out = r.render(n_total, clip[s:e].clone(), gather=gather, host_out=host)
+        out = r.render(n_total, clip[s:e].clone(), gather=gather, host_out=host if rank == 0 else None, to_host=to_host)
         if gather:
             ok = torch.equal(out, exp) and r.gather_mode == "nccl"       # CPU tensors: the collective path (gloo here)
             if to_host and rank == 0:
