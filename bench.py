@@ -542,6 +542,30 @@ def main():
         extras["gather_uint8"] = {"value": K * B * world / (t.item() / 1e3), "unit": "frames/s", "gather_mode": sr8.gather_mode,
                                   "bytes_received_per_step_per_rank": (world - 1) * B * H * W * 3}
         del sr8
+        # the collective fused into the conv kernel: the tail epilogue stores through the NVLink multicast mapping (NVLS)
+        try:
+            srm = ShardedRenderer(lambda fm_, out_: net.render(fm_, cand, out=out_), chunk=B, gather="mc",
+                                  render_ptr_fn=lambda fm_, ptr: net.render_into_ptr(fm_, cand, ptr))
+            srm.render(min(Wm, K) * B * world, local_fm[: min(Wm, K) * B])
+            barrier()
+            a.record()
+            clip_mc = srm.render(K * B * world, local_fm)
+            b.record()
+            barrier()
+            t = torch.tensor([a.elapsed_time(b)], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            err_mc = None
+            if rank == 0:
+                g = partition(K * B * world, world, world - 1)[0] + (K - 1) * B + (B - 1)
+                err_mc = oracle_err(clip_mc[g:g + 1], world - 1, K - 1, B - 1)
+            extras["gather_multicast_in_kernel"] = {
+                "value": K * B * world / (t.item() / 1e3), "unit": "frames/s", "gather_mode": srm.gather_mode,
+                "max_abs_err_vs_oracle_last_rank_last_frame": err_mc,
+                "note": "fp32 frames; the tail conv's float2 stores go through the symmetric buffer's multicast address, no copy "
+                        "or collective kernel follows"}
+            del srm, clip_mc
+        except Exception as exc:      # noqa: BLE001
+            extras["gather_multicast_in_kernel"] = {"unavailable": f"{type(exc).__name__}: {exc}"[:300]}
         if args.clip_frames > 0:
             n_tot = args.clip_frames
             s_, e_ = partition(n_tot, world, rank)

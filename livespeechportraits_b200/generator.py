@@ -222,8 +222,18 @@ class Feature2Face_G(nn.Module):
         (``(x+1)/2*255``, clip, truncate, HWC) instead of fp32 ``[B,3,H,W]`` - what demo.py:268 builds per frame."""
         return self.render(feature_map, cand_image, out=out, precision=precision, _uint8=True)
 
+    def render_into_ptr(self, feature_map: torch.Tensor, cand_image: Optional[torch.Tensor], out_ptr: int,
+                        precision: Optional[str] = None) -> None:
+        """``render`` with the fp32 ``[B,3,H,W]`` output written through a raw device address (8-byte aligned) instead of a
+        tensor: the address may be an NVLink *multicast* mapping (``torch.distributed._symmetric_memory`` handle
+        ``.multicast_ptr`` + offset), in which case every float2 store of the tail kernel's epilogue lands in the clip buffer
+        of EVERY rank - the all-gather happens inside the conv kernel (parallel.ShardedRenderer, gather="mc")."""
+        if int(out_ptr) % 8:
+            raise ValueError("out_ptr must be 8-byte aligned")
+        self.render(feature_map, cand_image, precision=precision, _out_ptr=int(out_ptr))
+
     def render(self, feature_map: torch.Tensor, cand_image: Optional[torch.Tensor], out: Optional[torch.Tensor] = None,
-               precision: Optional[str] = None, _uint8: bool = False) -> torch.Tensor:
+               precision: Optional[str] = None, _uint8: bool = False, _out_ptr: Optional[int] = None) -> torch.Tensor:
         """Fused ``torch.cat([feature_map, cand_image], 1)`` + generator (feature2face_model.py:231-233).
 
         ``cand_image`` may have batch 1 (broadcast over the frames, as demo.py:266 reuses one candidate set).
@@ -258,6 +268,14 @@ class Feature2Face_G(nn.Module):
         ws = self._workspace(b, h, w, mode)
         oshape, odtype = ((b, h, w, self.out_nc), torch.uint8) if _uint8 else ((b, self.out_nc, h, w), torch.float32)
         user_out = None
+        if _out_ptr is not None:
+            if _uint8 or out is not None:
+                raise ValueError("raw output address: fp32 frames only, no `out` tensor")
+            stream = torch.cuda.current_stream(feature_map.device).cuda_stream
+            _lib.check(self._lib.lspg_forward(self._handle, fm_ptr, fm_stride, cand_ptr, cand_stride, _out_ptr, b, h, w,
+                                              ws.data_ptr(), ws.numel(), mode, stream))
+            del hold
+            return None
         if out is None:
             out = torch.empty(oshape, dtype=odtype, device=feature_map.device)
         elif tuple(out.shape) != oshape or out.dtype != odtype or not out.is_contiguous():

@@ -15,6 +15,10 @@ Two implementations of the exchange, chosen by ``gather=``:
     copy engines move the bytes, no SM and no NCCL kernel runs next to the persistent conv kernels (round-1
     finding: the SM-resident NCCL all-gather slowed the convs by 9 % at 8 GPUs).  One cross-rank barrier at the end
     of the clip (or per chunk when frames are delivered to the host as they complete).
+``"mc"``  (opt-in, fp32 frames) - same symmetric clip buffer, but the tail kernel's output address is the buffer's NVLink
+    *multicast* mapping (NVLS): every float2 store of the conv epilogue lands in all ranks' buffers through the switch.  No
+    copy of any kind follows the conv kernel - the collective is fused into it.  Needs ``render_ptr_fn`` (a function that
+    renders to a raw device address, ``Feature2Face_G.render_into_ptr``) and multicast support on the node.
 ``"nccl"`` - ``all_gather_into_tensor`` per chunk on a side stream into a double-buffered staging tensor and a copy
     into clip order (the round-1 path; also what runs on CPU/gloo in the tests).
 
@@ -54,9 +58,13 @@ class ShardedRenderer:
     """
 
     def __init__(self, render_fn: Callable[[torch.Tensor, torch.Tensor], None], group=None, chunk: int = 32,
-                 uint8: bool = False, gather: str = "auto", copy_streams: int = 4):
-        if gather not in ("auto", "ce", "nccl"):
-            raise ValueError("gather must be 'auto', 'ce' or 'nccl'")
+                 uint8: bool = False, gather: str = "auto", copy_streams: int = 4,
+                 render_ptr_fn: Optional[Callable[[torch.Tensor, int], None]] = None):
+        if gather not in ("auto", "ce", "mc", "nccl"):
+            raise ValueError("gather must be 'auto', 'ce', 'mc' or 'nccl'")
+        if gather == "mc" and (render_ptr_fn is None or uint8):
+            raise ValueError("gather='mc' needs render_ptr_fn and fp32 frames (multicast stores are 8-byte float2 stores)")
+        self.render_ptr_fn = render_ptr_fn
         self.render_fn = render_fn
         self.group = group
         self.chunk = int(chunk)
@@ -101,23 +109,25 @@ class ShardedRenderer:
         if self.gather_mode is not None:
             return self.gather_mode
         mode, why = "nccl", None
-        if self.gather_request in ("auto", "ce") and dev.type == "cuda" and self.world > 1:
+        if self.gather_request in ("auto", "ce", "mc") and dev.type == "cuda" and self.world > 1:
             ok = 1
             try:
-                self._symmetric_clip(n_total, h, w, dev)
+                _, hdl_, _ = self._symmetric_clip(n_total, h, w, dev)
+                if self.gather_request == "mc" and not (hdl_.has_multicast_support and int(hdl_.multicast_ptr) != 0):
+                    raise RuntimeError("the symmetric allocation has no NVLink multicast mapping on this node")
             except Exception as exc:          # noqa: BLE001 - any failure means "not available here"
                 ok, why = 0, f"{type(exc).__name__}: {exc}"
             flag = torch.tensor([ok], device=dev, dtype=torch.int32)
             dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
             if int(flag.item()) == 1:
-                mode = "ce"
+                mode = "mc" if self.gather_request == "mc" else "ce"
             else:
                 why = why or "symmetric memory unavailable on another rank"
                 self._symm.clear()
-                if self.gather_request == "ce":
-                    raise RuntimeError(f"gather='ce' requested but symmetric memory is unavailable: {why}")
-        elif self.gather_request == "ce":
-            raise RuntimeError("gather='ce' needs CUDA devices and world_size > 1")
+                if self.gather_request in ("ce", "mc"):
+                    raise RuntimeError(f"gather={self.gather_request!r} requested but it is unavailable here: {why}")
+        elif self.gather_request in ("ce", "mc"):
+            raise RuntimeError(f"gather={self.gather_request!r} needs CUDA devices and world_size > 1")
         self.gather_mode, self.gather_fallback_reason = mode, why
         return mode
 
@@ -168,13 +178,13 @@ class ShardedRenderer:
                 d2h.synchronize()
             return out
         mode = self._decide_mode(n_total, h, w, dev)
-        if mode == "ce":
-            return self._render_ce(n_total, local_feature_maps, host_out, to_host)
+        if mode in ("ce", "mc"):
+            return self._render_ce(n_total, local_feature_maps, host_out, to_host, multicast=(mode == "mc"))
         return self._render_nccl(n_total, local_feature_maps, host_out)
 
     # ------------------------------------------------------------------ copy-engine push over symmetric memory
     def _render_ce(self, n_total: int, local_feature_maps: torch.Tensor, host_out: Optional[torch.Tensor],
-                   to_host: bool) -> torch.Tensor:
+                   to_host: bool, multicast: bool = False) -> torch.Tensor:
         dev = local_feature_maps.device
         h, w = local_feature_maps.shape[-2:]
         clip, hdl, peers = self._symmetric_clip(n_total, h, w, dev)
@@ -191,7 +201,11 @@ class ShardedRenderer:
         hdl.barrier(channel=0)
         for off, ln in chunk_schedule(n_max, self.chunk):
             mine = max(0, min(ln, n_local - off))
-            if mine > 0:
+            if mine > 0 and multicast:
+                # the tail kernel stores through the multicast mapping: its float2 stores reach every rank's clip buffer
+                frame_bytes = clip[0].numel() * clip.element_size()
+                self.render_ptr_fn(local_feature_maps[off:off + mine], int(hdl.multicast_ptr) + (start + off) * frame_bytes)
+            elif mine > 0:
                 lo = start + off
                 self.render_fn(local_feature_maps[off:off + mine], clip[lo:lo + mine])      # tail kernel -> clip buffer
                 ready = torch.cuda.Event()

@@ -50,9 +50,10 @@ def main():
                 if mine > 0:
                     fn(fm_all[rs + off:rs + off + mine].to(dev), exp[rs + off:rs + off + mine])
         torch.cuda.synchronize()
-        for mode in ("ce", "nccl"):
+        for mode in (("ce", "nccl") if uint8 else ("ce", "mc", "nccl")):
             try:
-                sr = ShardedRenderer(fn, chunk=chunk, uint8=uint8, gather=mode)
+                sr = ShardedRenderer(fn, chunk=chunk, uint8=uint8, gather=mode,
+                                     render_ptr_fn=(lambda f, ptr: net.render_into_ptr(f, cand_d, ptr)) if mode == "mc" else None)
                 host = torch.empty(shape, dtype=exp.dtype).pin_memory() if rank == 0 else None
                 t0 = time.perf_counter()
                 got = sr.render(n_total, fm_all[s:e].to(dev), host_out=host, to_host=True)
@@ -68,7 +69,8 @@ def main():
                 ok_all = ok_all and same and host_ok and same2
             except Exception as exc:      # noqa: BLE001
                 print(f"[rank {rank}] uint8={uint8} gather={mode}: FAILED {type(exc).__name__}: {exc}", flush=True)
-                ok_all = False
+                if not (mode == "mc" and "unavailable" in str(exc)):       # no NVLink multicast on this node: reported, not a failure
+                    ok_all = False
         if rank == 0 and not uint8:
             for i in (0, n_total // 2, n_total - 1):
                 x = torch.cat([fm_all[i:i + 1], cand[:1]], 1)
