@@ -534,8 +534,14 @@ Geo layer_geo(const lspg_ctx* h, const Layer& L, int B, int H, int W) {
     // Cluster split-K: the 2 / 4 / 8 CTAs of a tile form a cluster, exchange their partial rows through distributed shared
     // memory and finish the tile themselves - no partials in global memory, no finisher launch.  Needs exactly `cs`
     // non-empty K ranges and tiles x cs CTAs in one wave.
-    static const bool no_csplit = getenv("LSPG_NO_CLUSTER_SPLIT") != nullptr;
-    if (!no_csplit && want > 1) {
+    // Measured on one B200 (profiles/r02_t3_ab_cluster_split.txt, alternating runs): 32 frames per step 15.57-15.67 ms with
+    // the cluster reduction vs 15.77-15.82 ms with finisher kernels (-1 %); one frame per call 1.283 vs 1.262 ms (+1.7 %: at
+    // batch 1 a cluster of 8 leaves 64 CTAs streaming the layer's weights where 18 finisher-splits keep 144 busy, and under
+    // PDL the finisher launches were almost free).  So clusters from 8 frames up, finishers below; LSPG_CLUSTER_SPLIT=0/1
+    // forces either for A/B runs.
+    static const int csplit_env = [] { const char* e = getenv("LSPG_CLUSTER_SPLIT"); return e ? atoi(e) : -1; }();
+    const bool use_csplit = csplit_env >= 0 ? csplit_env != 0 : B >= 8;
+    if (use_csplit && want > 1) {
       for (int cs : {8, 4, 2}) {
         if (cs > want) continue;
         const int len = (g.k_items + cs - 1) / cs;

@@ -5,8 +5,8 @@ timeout 1500 python -m pytest tests -m gpu -q -s -x > gpurun_out/pytest_gpu.log 
 timeout 200 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log
 for B in 1 32; do
   for i in 1 2; do
-    echo "## cluster-split B$B" >> gpurun_out/ab_csplit.log; timeout 200 python tests/gpu_bringup.py time large A parity 512 $B >> gpurun_out/ab_csplit.log 2>&1
-    echo "## finisher B$B" >> gpurun_out/ab_csplit.log; LSPG_NO_CLUSTER_SPLIT=1 timeout 200 python tests/gpu_bringup.py time large A parity 512 $B >> gpurun_out/ab_csplit.log 2>&1
+    echo "## cluster-split B$B" >> gpurun_out/ab_csplit.log; LSPG_CLUSTER_SPLIT=1 timeout 200 python tests/gpu_bringup.py time large A parity 512 $B >> gpurun_out/ab_csplit.log 2>&1
+    echo "## finisher B$B" >> gpurun_out/ab_csplit.log; LSPG_CLUSTER_SPLIT=0 timeout 200 python tests/gpu_bringup.py time large A parity 512 $B >> gpurun_out/ab_csplit.log 2>&1
   done
 done
 LSPG_PER_LAYER=1 timeout 300 python tests/gpu_bringup.py time large A parity 512 1 > gpurun_out/b1_layers.log 2>&1
