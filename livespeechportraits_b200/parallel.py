@@ -89,20 +89,34 @@ class ShardedRenderer:
     def _symmetric_clip(self, n_total: int, h: int, w: int, dev: torch.device):
         """Clip buffer mapped into every rank + views of every peer's copy.  Collective: every rank calls it with the same
         arguments in the same order.  Raises if symmetric memory is unavailable (caller falls back to NCCL)."""
-        key = (n_total, h, w, self.uint8)
+        key = (h, w, self.uint8)
         hit = self._symm.get(key)
-        if hit is not None:
-            return hit
+        if hit is not None and hit[0] >= n_total:     # one allocation serves every clip up to its capacity
+            cap, clip, hdl, peers = hit
+            return clip[:n_total], hdl, [p_[:n_total] for p_ in peers]
         import torch.distributed._symmetric_memory as symm_mem
+        self._symm.pop(key, None)                     # growing: release the smaller buffer first
         shape = (n_total,) + self._frame_shape(h, w)
         clip = symm_mem.empty(*shape, dtype=self._dtype(), device=dev)
         grp = self.group if self.group is not None else dist.group.WORLD
         hdl = symm_mem.rendezvous(clip, grp)
         peers = [clip if r == self.rank else hdl.get_buffer(r, shape, self._dtype()) for r in range(self.world)]
-        if len(self._symm) >= 2:                      # a clip buffer is large: keep at most two shapes alive
+        if len(self._symm) >= 2:                      # a clip buffer is large: keep at most two frame shapes alive
             self._symm.pop(next(iter(self._symm)))
-        self._symm[key] = (clip, hdl, peers)
-        return self._symm[key]
+        self._symm[key] = (n_total, clip, hdl, peers)
+        return clip, hdl, peers
+
+    def prepare(self, n_total: int, height: int, width: int, device: torch.device) -> str:
+        """Collective, optional: decide the exchange mode and allocate + rendezvous the symmetric clip buffer for clips of up
+        to ``n_total`` frames now (hundreds of milliseconds for a multi-GB buffer) instead of inside the first ``render``.
+        Returns the mode that will run ("ce", "mc" or "nccl")."""
+        if self.world == 1:
+            return "local"
+        dev = torch.device(device)
+        mode = self._decide_mode(n_total, height, width, dev)
+        if mode in ("ce", "mc"):
+            self._symmetric_clip(n_total, height, width, dev)       # grows the buffer if an earlier clip was shorter
+        return mode
 
     def _decide_mode(self, n_total: int, h: int, w: int, dev: torch.device) -> str:
         """"ce" needs CUDA + symmetric memory on every rank; agreement is reached with one tiny all-reduce."""
