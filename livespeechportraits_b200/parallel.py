@@ -95,6 +95,8 @@ class ShardedRenderer:
             cap, clip, hdl, peers = hit
             return clip[:n_total], hdl, [p_[:n_total] for p_ in peers]
         import torch.distributed._symmetric_memory as symm_mem
+        if self._symm:
+            torch.cuda.synchronize(dev)               # nothing in flight may still touch a buffer that is about to be released
         self._symm.pop(key, None)                     # growing: release the smaller buffer first
         shape = (n_total,) + self._frame_shape(h, w)
         clip = symm_mem.empty(*shape, dtype=self._dtype(), device=dev)
