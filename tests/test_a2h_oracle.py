@@ -184,3 +184,23 @@ def test_c_abi_exports_and_argument_checks():
         headpose.HeadposeGenerator(opt, A.make_state_dict(opt, "A"), device=torch.device("cpu"))
     with pytest.raises(NotImplementedError):
         headpose.config_from_opt(A.default_opt(feature_decoder="LSTM"))
+
+
+@pytest.mark.skipif(not A.reference_available(), reason="reference checkout not present on this machine")
+def test_install_swaps_the_loop_on_the_reference_model_class():
+    """headpose.install() replaces Audio2HeadposeModel.generate_sequences (what demo.py:212 calls); the model object, its
+    module and weights stay the reference's own.  Without a GPU the swapped loop refuses to run (no CPU path)."""
+    opt = A.default_opt()
+    m = A.reference_model(opt, A.make_state_dict(opt, "A"))
+    import models.audio2headpose_model as ref_mod  # type: ignore
+    original = ref_mod.Audio2HeadposeModel.generate_sequences
+    try:
+        headpose.install()
+        assert ref_mod.Audio2HeadposeModel.generate_sequences is headpose.generate_sequences
+        audio = A.make_audio_feats(30, opt)
+        assert m.generate_sequences(audio, np.zeros(12, np.float32), fill_zero=False, sigma_scale=0.3, opt=opt) is None   # :161-162
+        if not torch.cuda.is_available():
+            with pytest.raises(RuntimeError, match="no CPU path"):
+                m.generate_sequences(audio, np.zeros(12, np.float32), fill_zero=True, sigma_scale=0.3, opt=opt)
+    finally:
+        ref_mod.Audio2HeadposeModel.generate_sequences = original
