@@ -48,8 +48,9 @@ def parse():
     ap.add_argument("--width", type=int, default=512)
     ap.add_argument("--gather", default="auto", choices=["auto", "ce", "nccl"],
                     help="N > 1: how rendered frames reach every rank (parallel.ShardedRenderer)")
-    ap.add_argument("--clip-frames", type=int, default=0,
-                    help="N > 1: also render a clip of exactly this many frames (configs[3]: 10000) and report it as clip_run")
+    ap.add_argument("--clip-frames", type=int, default=10000,
+                    help="N > 1: also render one clip of exactly this many frames and report it as clip_run (BASELINE.json "
+                         "configs[3]: 10000 synthetic frames, frame-sharded; 0 = skip)")
     ap.add_argument("--no-extras", action="store_true", help="skip the side measurements (other modes / configs, library baseline)")
     return ap.parse_args()
 
