@@ -22,7 +22,7 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     sys.path.insert(0, ROOT)
     import bench
     import types
-    args = types.SimpleNamespace(variant="large", batch=64, height=512, width=512, mode="parity")
+    args = types.SimpleNamespace(variant="large", batch=32, height=512, width=512, mode="parity")
     assert d["config"] == bench.config_dict(args, 1)
     assert d["cpu_baseline"]["host"]["usable_cpus"] >= 1 and "sample" in d["cpu_baseline"]
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]

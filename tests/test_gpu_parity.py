@@ -206,7 +206,7 @@ def test_clip_renderer_pipeline_matches_direct_calls():
 
 @pytest.mark.parametrize("recipe,batch", [("A", 64), ("B", 64), ("A", 32), ("B", 32), ("A", 16), ("B", 16)])
 def test_large_512_at_the_benchmarked_batch_sizes(recipe, batch):
-    """The plan bench.py times (large, 512x512, 64 frames per step by default; 32 and 16 = the other tile/wave choices of layer_geo) is the plan
+    """The plan bench.py times (large, 512x512, 32 frames per step by default; 64 and 16 = other tile/wave choices of layer_geo) is the plan
     that is gated: first, middle and last frame of the batch against the oracle at the 1e-3 contract, recipe A and the
     amplifying recipe B, plus the fused-tensor2im uint8 output of the same plan."""
     net, sd = get_net("large", recipe)
