@@ -134,7 +134,7 @@ def draw_reference_noise(nframe: int, ndim: int, ncenter: int):
     return noise, uniform
 
 
-_GENERATORS: "Dict[int, HeadposeGenerator]" = {}
+_GENERATORS: "Dict[int, tuple]" = {}          # id(module) -> (HeadposeGenerator, stamp of the module's tensors)
 
 
 def generate_sequences(self, audio_feats, pre_headpose, fill_zero=True, sigma_scale=0.0, opt=[]):   # noqa: B006 - reference signature
@@ -145,11 +145,20 @@ def generate_sequences(self, audio_feats, pre_headpose, fill_zero=True, sigma_sc
     if not fill_zero:
         return None                                                                    # audio2headpose_model.py:161-162
     net = self.Audio2Headpose.module if hasattr(self.Audio2Headpose, "module") else self.Audio2Headpose
-    gen = _GENERATORS.get(id(net))
-    if gen is None:
-        gen = HeadposeGenerator(opt, net.state_dict())
+    sd = net.state_dict()
+    # the packed copy on the device is reused while the module's tensors are untouched: tensor version counters move on every
+    # in-place write (load_state_dict copies in place, optimiser steps, init_weights), data pointers on re-allocation (.to())
+    stamp = tuple((v.data_ptr(), v._version) for v in sd.values())
+    hit = _GENERATORS.get(id(net))
+    if hit is None or hit[1] != stamp:
+        if hit is None:
+            gen = HeadposeGenerator(opt, sd)
+        else:
+            gen = hit[0]
+            gen.load_state_dict(sd)
         _GENERATORS.clear()
-        _GENERATORS[id(net)] = gen
+        _GENERATORS[id(net)] = (gen, stamp)
+    gen = _GENERATORS[id(net)][0]
     audio = np.asarray(audio_feats, dtype=np.float32).reshape(-1, 512 * 2)              # :148
     nframe = audio.shape[0] - opt.frame_future
     if getattr(opt, "loss", "GMM") == "GMM":

@@ -90,6 +90,14 @@ def test_drop_in_generate_sequences_keeps_signature_and_random_stream():
     ref = A.generate_sequences(sd, audio, pre, A.reference_noise(33, 12, 1, seed=21), opt, 0.3)
     assert np.abs(out - ref).max() <= TOL
     assert headpose.generate_sequences(model, audio, pre, fill_zero=False, sigma_scale=0.3, opt=opt) is None
+    # new weights in the SAME module object (load_state_dict copies in place): the cached device copy must follow
+    sd2 = A.make_state_dict(opt, "B", 9)
+    for k in sd:
+        sd[k].copy_(sd2[k])
+    torch.manual_seed(21)
+    out2 = headpose.generate_sequences(model, audio.reshape(-1), pre, fill_zero=True, sigma_scale=0.3, opt=opt)
+    ref2 = A.generate_sequences(sd2, audio, pre, A.reference_noise(33, 12, 1, seed=21), opt, 0.3)
+    assert np.abs(out2 - ref2).max() <= TOL and np.abs(out2 - out).max() > 1e-3
 
 
 def test_l2_loss_and_two_component_mixture():
