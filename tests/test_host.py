@@ -331,3 +331,54 @@ def test_package_exports_public_names():
     import livespeechportraits_b200 as pkg
     for name in ("Feature2Face_G", "install", "ClipRenderer", "ShardedRenderer", "partition"):
         assert hasattr(pkg, name)
+
+
+def test_planner_invariants_over_random_problem_sizes():
+    """Property test of layer_geo / workspace sizing through the C ABI (host only): any accepted (batch, H, W) gives tiles
+    that cover every level, split-K that stays inside one wave with non-empty K ranges, cluster splits of portable size, and a
+    workspace at least as large as the activations + the largest partial buffer."""
+    from hypothesis import given, settings, strategies as st
+    lib = _lib.load()
+    handles = {}
+    for variant in ("normal", "large"):
+        h = C.c_void_p()
+        assert lib.lspg_create(C.byref(h), _lib.LSPG_VARIANT[variant], 64, 8, 13, 3, -1) == 0
+        n = C.c_int()
+        lib.lspg_num_layers(h, C.byref(n))
+        handles[variant] = (h, n.value)
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.sampled_from(["normal", "large"]), st.integers(1, 96), st.sampled_from([256, 512, 1024]), st.sampled_from([256, 512, 1024]),
+           st.sampled_from([0, 1]))
+    def check(variant, batch, hh, ww, mode):
+        h, nl = handles[variant]
+        need = C.c_size_t()
+        assert lib.lspg_workspace_bytes(h, batch, hh, ww, mode, C.byref(need)) == 0, lib.lspg_last_error()
+        act = 0
+        nt = C.c_int()
+        lib.lspg_num_tensors(h, C.byref(nt))
+        for t in range(nt.value):
+            c, th, tw = C.c_int(), C.c_int(), C.c_int()
+            lib.lspg_tensor_shape(h, t, hh, ww, C.byref(c), C.byref(th), C.byref(tw))
+            act += batch * th.value * tw.value * c.value * 2 * (2 if mode == 1 else 1)
+        worst_partial = 0
+        for i in range(nl):
+            g = _lib.LspgLayerGeo()
+            assert lib.lspg_debug_layer_geo(h, i, batch, hh, ww, C.byref(g)) == 0
+            assert g.tile_w * g.tile_h * g.tile_n == 128 and g.m_tiles >= 1 and g.n_tiles >= 1
+            tiles = g.m_tiles * g.n_tiles * g.n_phases
+            assert 1 <= g.ctas <= 148
+            if g.n_split > 1:
+                assert tiles * g.n_split <= 148 and (g.n_split - 1) * g.split_len < g.k_items <= g.n_split * g.split_len
+                assert g.cluster_split in (0, 2, 4, 8) and (g.cluster_split == 0 or g.cluster_split == g.n_split)
+                assert (g.cluster_split != 0) == (batch >= 8) or g.partial_bytes > 0
+            if g.kernel == 2:
+                assert g.m_tiles % 2 == 0 and g.ctas % 2 == 0 and g.n_split == 1
+            worst_partial = max(worst_partial, g.partial_bytes)
+        assert need.value >= act + worst_partial
+
+    try:
+        check()
+    finally:
+        for h, _ in handles.values():
+            lib.lspg_destroy(h)
