@@ -1,6 +1,6 @@
 #!/bin/bash
 # A/B a bring-up switch with alternating runs on the SAME box (box-to-box variation is +-3 %, larger than most effects).
-# Usage under gpurun:  bash tests/gpu_scripts/ab.sh "LSPG_NO_WAVE_RULE=1" [batch] [mode] [rounds]
+# Usage under gpurun:  bash tests/gpu_scripts/ab.sh "LSPG_CLUSTER_SPLIT=0" [batch] [mode] [rounds]
 # Prints the ms/forward of every run and the medians.
 mkdir -p gpurun_out
 VAR="$1"; B=${2:-32}; MODE=${3:-parity}; N=${4:-3}
